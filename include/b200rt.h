@@ -1,0 +1,87 @@
+/* b200rt -- C ABI of the in-box B200 runtime behind the `modal` shim's .map() fan-out.
+ *
+ * The reference (modal-labs/modal-examples) has no native interface for this path: its fan-out is
+ *   Function.map  -> cloudpickle -> gRPC -> one container per input -> gather
+ * as used at 06_gpu_and_ml/embeddings/text_embeddings_inference.py:167 (`model.embed.map(...)`), and its
+ * arithmetic is an HTTP call into an un-vendored TEI server (`POST /embed`, same file :100).  The entry
+ * points below are what a binding for that path replaces; each cites the reference interface it stands
+ * in for.  Plain pointers and sizes only; every function is thread-safe; nothing calls back into the
+ * caller.  Return 0 on success, a negative B200RT_E_* code on failure (text via b200rt_last_error()).
+ */
+#ifndef B200RT_H
+#define B200RT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RT_OK 0
+#define B200RT_TIMEOUT 1        /* b200rt_wait: not complete within timeout_ms; b200rt_poll_any: none ready */
+#define B200RT_E_INVALID (-1)   /* bad argument (shape, id out of vocabulary, unknown handle) */
+#define B200RT_E_STATE (-2)     /* not initialised / already initialised / shut down */
+#define B200RT_E_CUDA (-3)      /* CUDA error; the context is poisoned and every later call fails fast */
+#define B200RT_E_NOMEM (-4)
+#define B200RT_E_UNSUPPORTED (-5) /* e.g. device is not sm_100, or geometry is not BERT-base */
+
+/* Geometry of a BERT encoder (HF BertConfig fields).  The sm_100a kernels are specialised for the
+ * BGE-base geometry (hidden 768, 12 heads of 64, inter 3072, max_pos <= 512); `layers` is free.   */
+typedef struct b200rt_bert_config {
+    int32_t vocab, hidden, layers, heads, inter, max_pos, type_vocab;
+    float eps;
+} b200rt_bert_config;
+
+typedef struct b200rt_stats_t {
+    uint64_t items, waves, tickets;     /* completed so far */
+    uint64_t kernel_launches;           /* of this library's own kernels */
+    uint64_t h2d_bytes, d2h_bytes;      /* through submit()/wait() */
+    uint64_t peer_bytes;                /* scatter + fused-gather bytes that crossed NVLink */
+    double stage_us, h2d_scatter_us, forward_us, d2h_us; /* summed per-wave stage times (device events) */
+} b200rt_stats_t;
+
+/* Replica pool.  Stands in for `@app.cls(gpu=..., max_containers=N)` + `@modal.concurrent`
+ * (text_embeddings_inference.py:79-86): n_gpus local B200s instead of N cloud containers.  Enables peer
+ * access between all of them and starts the scheduler threads.  devices = NULL means 0..n_gpus-1.    */
+int b200rt_init(int n_gpus, uint32_t flags);
+int b200rt_init_devices(const int* devices, int n_gpus, uint32_t flags);
+int b200rt_num_gpus(void);
+
+/* Cold start.  Stands in for `download_model` / `spawn_server` (text_embeddings_inference.py:37-56):
+ * one host->root-GPU copy of the fp32 weight blob, fp16 conversion on the GPU, then a peer broadcast
+ * over NVLink to the other replicas.  kind = "bert".  Blob order: see DESIGN.md / oracle blob_layout. */
+int b200rt_model_load(const char* kind, const void* cfg, const void* weights, size_t nbytes, int* model_out);
+
+/* One .map() input.  Stands in for `TextEmbeddingsInference.embed` -> `POST /embed`
+ * (text_embeddings_inference.py:97-104) with token ids instead of strings: ids is [n_items, max_len]
+ * int32 row-major (positions >= lens[i] are ignored; lens == NULL means every item is max_len long),
+ * out receives [n_items, hidden] fp32 unit-norm embeddings.  Host buffers; `out` stays caller-owned and
+ * must remain valid until the ticket completes; ids/lens may be reused as soon as submit returns.     */
+int b200rt_submit(int model, const int32_t* ids, const int32_t* lens, int n_items, int max_len, float* out,
+                  uint64_t* ticket_out);
+/* Completion, ordered (`order_outputs=True`) ...                                                      */
+int b200rt_wait(uint64_t ticket, int timeout_ms); /* timeout_ms < 0: forever */
+/* ... and unordered (`order_outputs=False`, text_embeddings_inference.py:167): next finished ticket
+ * that nobody has waited on yet; B200RT_TIMEOUT when none is ready within timeout_ms.                 */
+int b200rt_poll_any(uint64_t* ticket_out, int timeout_ms);
+
+/* Device-resident variant for callers that already hold the batch in HBM on replica `gpu` (index into
+ * the pool): enqueues the forward of one batch on `stream` (a cudaStream_t; NULL = the replica's own
+ * compute stream) and returns without synchronising.  n_items * max_len must fit the wave capacity.  */
+int b200rt_embed_device(int model, int gpu, const int32_t* d_ids, const int32_t* d_lens, int n_items, int max_len,
+                        float* d_out, void* stream);
+int b200rt_device_sync(int gpu);
+int b200rt_wave_capacity_items(void); /* items of 512 tokens one replica takes per wave */
+
+void* b200rt_alloc_pinned(size_t nbytes);
+void b200rt_free_pinned(void* p);
+
+int b200rt_stats(b200rt_stats_t* out);
+const char* b200rt_last_error(void); /* thread-local */
+void b200rt_shutdown(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RT_H */

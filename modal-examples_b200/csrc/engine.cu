@@ -1,0 +1,1051 @@
+// b200rt engine: replica pool, cold-start weight broadcast, the per-shard BERT forward, the C++ stream
+// scheduler behind Function.map, and the C ABI declared in include/b200rt.h.
+//
+// Threads: callers (any number, any thread) -> submit queue -> dispatcher (forms waves, stages ids into
+// pinned memory, H2D to the root GPU, scatter kernel into peer HBM, enqueues each shard's forward, whose
+// last kernel stores straight into the root's gather buffer, then one D2H) -> completer (waits the wave's
+// event, hands rows to the tickets' caller-owned buffers, wakes waiters).  No NCCL call and no host
+// round-trip between H2D and D2H.
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/b200rt.h"
+#include "../../include/b200rt_debug.h"
+#include "kernels.h"
+
+namespace b200 {
+cudaError_t gemm_init_device();
+cudaError_t attention_init_device();
+cudaError_t kernels_init_device() {
+    cudaError_t e = gemm_init_device();
+    if (e != cudaSuccess) return e;
+    return attention_init_device();
+}
+}  // namespace b200
+
+using namespace b200;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ errors
+
+thread_local std::string t_last_error;
+std::atomic<bool> g_poisoned{false};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_last_error = buf;
+    if (code == B200RT_E_CUDA) g_poisoned.store(true);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                      \
+    do {                                                                                                    \
+        cudaError_t _e = (expr);                                                                            \
+        if (_e != cudaSuccess)                                                                              \
+            return fail(B200RT_E_CUDA, "%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ tensor maps
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int load_driver_entry() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+        return fail(B200RT_E_CUDA, "cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return 0;
+}
+
+// fp16 2D row-major [rows, cols] -> box {64, box_rows}, 128B swizzle
+int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200RT_E_CUDA, "cuTensorMapEncodeTiled(2d %llu x %llu) -> %d",
+                                       (unsigned long long)rows, (unsigned long long)cols, (int)r);
+    return 0;
+}
+
+// fp16 qkv [B, S, 2304] -> box {64, 128, 1}, 128B swizzle (rows past S are zero-filled)
+int make_map_qkv(CUtensorMap* m, const void* base, uint64_t B, uint64_t S) {
+    cuuint64_t dims[3] = {QKV_DIM, S, B};
+    cuuint64_t strides[2] = {QKV_DIM * 2, S * QKV_DIM * 2};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200RT_E_CUDA, "cuTensorMapEncodeTiled(qkv B=%llu S=%llu) -> %d",
+                                       (unsigned long long)B, (unsigned long long)S, (int)r);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ model / device state
+
+constexpr int NSLOT = 3;
+constexpr int MAX_SEQ = 512;
+
+struct LayerW {
+    __half *qkv_w, *ao_w, *ff1_w, *ff2_w;
+    float *qkv_b, *ao_b, *ln1_g, *ln1_b, *ff1_b, *ff2_b, *ln2_g, *ln2_b;
+    CUtensorMap m_qkv, m_ao, m_ff1, m_ff2;
+};
+
+struct DevWeights {
+    float* f32_arena = nullptr;  // embeddings, biases, LayerNorm params
+    __half* f16_arena = nullptr; // GEMM weights
+    float *word, *pos, *type, *emb_g, *emb_b;
+    std::vector<LayerW> layers;
+};
+
+struct Model {
+    b200rt_bert_config cfg;
+    size_t f32_elems = 0, f16_elems = 0;
+    std::vector<DevWeights> per_dev;
+};
+
+struct Dev {
+    int id = -1;
+    int sm_count = 148;
+    cudaStream_t compute = nullptr;
+    // workspace (capacity cap_rows rows)
+    float *x32 = nullptr, *y32 = nullptr;
+    __half *x16 = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr;
+    CUtensorMap m_x16, m_ctx, m_ffn;
+    std::unordered_map<int, CUtensorMap> m_qkv_by_S;
+    // wave input slots (written by the root's scatter kernel, possibly over NVLink)
+    int32_t* ids_in[NSLOT] = {nullptr, nullptr, nullptr};
+    int32_t* lens_in[NSLOT] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_done[NSLOT];
+    std::mutex mu;  // serialises host-side enqueue on this replica (scheduler vs. embed_device/debug)
+};
+
+struct Ticket {
+    uint64_t id;
+    int model;
+    std::vector<int32_t> ids;   // private copy [n, S]
+    std::vector<int32_t> lens;
+    int n_items, S;
+    float* out;
+    int next_item = 0;          // dispatcher cursor
+    std::atomic<int> remaining; // items not yet delivered
+    bool done = false, claimed = false;
+    int status = 0;
+    std::string error;
+};
+
+struct Segment {
+    std::shared_ptr<Ticket> t;
+    int ticket_off, count, wave_off;
+};
+
+struct Wave {
+    int slot;
+    int n_items, S;
+    std::vector<Segment> segs;
+};
+
+struct Runtime {
+    std::vector<std::unique_ptr<Dev>> devs;
+    int cap_items = 64;  // per replica per wave, at 512 tokens
+    int cap_rows = 0;    // cap_items*512 rounded up to 128
+    std::vector<std::unique_ptr<Model>> models;
+    // root staging per slot
+    int32_t *h_ids[NSLOT], *h_lens[NSLOT];
+    float* h_out[NSLOT];
+    int32_t *d_ids_stage[NSLOT], *d_lens_stage[NSLOT];
+    float* d_out_gather[NSLOT];
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // on root
+    cudaEvent_t ev_scatter[NSLOT], ev_wave[NSLOT], ev_t0[NSLOT], ev_fwd_end[NSLOT];
+    // queues
+    std::mutex mu;
+    std::condition_variable cv_submit, cv_done, cv_slot, cv_wave;
+    std::deque<std::shared_ptr<Ticket>> pending;
+    std::unordered_map<uint64_t, std::shared_ptr<Ticket>> tickets;
+    std::deque<uint64_t> finished_unclaimed;
+    std::deque<Wave> inflight;
+    bool slot_busy[NSLOT] = {false, false, false};
+    uint64_t next_ticket = 1, next_wave = 0;
+    bool stopping = false;
+    std::thread dispatcher, completer;
+    b200rt_stats_t stats{};
+    std::mutex stats_mu;
+    std::string async_error;
+};
+
+std::mutex g_rt_mu;
+Runtime* g_rt = nullptr;
+
+// ------------------------------------------------------------------------------------------ forward
+
+struct Prof {
+    std::vector<std::string> names;
+    std::vector<cudaEvent_t> evs;
+};
+
+int get_qkv_map(Dev& d, int S, const CUtensorMap** out) {
+    auto it = d.m_qkv_by_S.find(S);
+    if (it == d.m_qkv_by_S.end()) {
+        CUtensorMap m;
+        const uint64_t B = static_cast<uint64_t>(g_rt->cap_rows) / S;
+        int rc = make_map_qkv(&m, d.qkv, B, S);
+        if (rc) return rc;
+        it = d.m_qkv_by_S.emplace(S, m).first;
+    }
+    *out = &it->second;
+    return 0;
+}
+
+// Enqueue the forward of one padded batch [B, S] on `stream`.  out: fp32 [B, 768], may be peer memory.
+// n_layers < cfg.layers (debug): stop early and leave the post-LN hidden state in d.x32.
+int forward(Dev& d, const Model& m, int dev_index, const int32_t* ids, const int32_t* lens, int B, int S, float* out,
+            cudaStream_t stream, int n_layers = -1, Prof* prof = nullptr, uint64_t* launches = nullptr) {
+    const DevWeights& w = m.per_dev[dev_index];
+    const b200rt_bert_config& c = m.cfg;
+    const int L = n_layers < 0 ? c.layers : n_layers;
+    const bool full = n_layers < 0;
+    const int M = B * S;
+    if (M > g_rt->cap_rows) return fail(B200RT_E_INVALID, "batch of %d x %d tokens exceeds wave capacity %d rows", B, S, g_rt->cap_rows);
+    const CUtensorMap* mq = nullptr;
+    if (int rc = get_qkv_map(d, S, &mq)) return rc;
+    uint64_t nl = 0;
+    auto mark = [&](const char* name) {
+        if (prof) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            cudaEventRecord(e, stream);
+            prof->names.push_back(name);
+            prof->evs.push_back(e);
+        }
+    };
+    mark("begin");
+    CUDA_TRY(launch_embed_ln(ids, w.word, w.pos, w.type, w.emb_g, w.emb_b, d.x32, d.x16, M, S, c.vocab, c.eps, stream));
+    ++nl; mark("embed_ln");
+    for (int l = 0; l < L; ++l) {
+        const LayerW& lw = w.layers[l];
+        CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_x16, lw.m_qkv, lw.qkv_b, nullptr, d.qkv, M, QKV_DIM, HIDDEN, d.sm_count, stream));
+        ++nl; mark("gemm_qkv");
+        CUDA_TRY(launch_attention(*mq, lens, d.ctx, B, S, stream));
+        ++nl; mark("attention");
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_F32, d.m_ctx, lw.m_ao, lw.ao_b, d.x32, d.y32, M, HIDDEN, HIDDEN, d.sm_count, stream));
+        ++nl; mark("gemm_attn_out");
+        CUDA_TRY(launch_ln(d.y32, lw.ln1_g, lw.ln1_b, d.x32, d.x16, M, c.eps, stream));
+        ++nl; mark("ln1");
+        CUDA_TRY(launch_gemm(EPI_BIAS_GELU_F16, d.m_x16, lw.m_ff1, lw.ff1_b, nullptr, d.ffn, M, c.inter, HIDDEN, d.sm_count, stream));
+        ++nl; mark("gemm_ffn1_gelu");
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_F32, d.m_ffn, lw.m_ff2, lw.ff2_b, d.x32, d.y32, M, HIDDEN, c.inter, d.sm_count, stream));
+        ++nl; mark("gemm_ffn2");
+        if (!(full && l == L - 1)) {
+            CUDA_TRY(launch_ln(d.y32, lw.ln2_g, lw.ln2_b, d.x32, d.x16, M, c.eps, stream));
+            ++nl; mark("ln2");
+        }
+    }
+    if (full) {
+        const LayerW& lw = w.layers[L - 1];
+        CUDA_TRY(launch_pool_normalize(d.y32, lw.ln2_g, lw.ln2_b, out, B, S, c.eps, stream));
+        ++nl; mark("pool_normalize");
+    }
+    if (launches) *launches += nl;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------ scheduler
+
+void finish_ticket_locked(Runtime& rt, const std::shared_ptr<Ticket>& t, int status, const std::string& err) {
+    if (t->done) return;
+    t->done = true;
+    t->status = status;
+    t->error = err;
+    rt.finished_unclaimed.push_back(t->id);
+    rt.stats.tickets++;
+}
+
+void fail_all(Runtime& rt, const std::string& err) {
+    std::lock_guard<std::mutex> lk(rt.mu);
+    rt.async_error = err;
+    for (auto& kv : rt.tickets) finish_ticket_locked(rt, kv.second, B200RT_E_CUDA, err);
+    rt.pending.clear();
+    rt.cv_done.notify_all();
+}
+
+#define SCHED_TRY(expr)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (expr);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            g_poisoned.store(true);                                                                  \
+            fail_all(rt, std::string(#expr) + ": " + cudaGetErrorString(_e));                        \
+            return;                                                                                  \
+        }                                                                                            \
+    } while (0)
+
+void dispatcher_main(Runtime* rtp) {
+    Runtime& rt = *rtp;
+    const int G = static_cast<int>(rt.devs.size());
+    Dev& root = *rt.devs[0];
+    for (;;) {
+        Wave wv;
+        {
+            std::unique_lock<std::mutex> lk(rt.mu);
+            rt.cv_submit.wait(lk, [&] { return rt.stopping || !rt.pending.empty(); });
+            if (rt.stopping) return;
+            // a free slot
+            int slot = static_cast<int>(rt.next_wave % NSLOT);
+            rt.cv_slot.wait(lk, [&] { return rt.stopping || !rt.slot_busy[slot]; });
+            if (rt.stopping) return;
+            if (rt.pending.empty()) continue;
+            rt.slot_busy[slot] = true;
+            rt.next_wave++;
+            wv.slot = slot;
+            wv.S = rt.pending.front()->S;
+            wv.n_items = 0;
+            const int model = rt.pending.front()->model;
+            // token capacity scales with 512/S: a wave holds cap_rows tokens per replica
+            const int cap_items_S = (rt.cap_rows / wv.S) * G;
+            while (!rt.pending.empty() && wv.n_items < cap_items_S) {
+                auto t = rt.pending.front();
+                if (t->S != wv.S || t->model != model) break;
+                const int take = std::min(t->n_items - t->next_item, cap_items_S - wv.n_items);
+                wv.segs.push_back(Segment{t, t->next_item, take, wv.n_items});
+                t->next_item += take;
+                wv.n_items += take;
+                if (t->next_item == t->n_items) rt.pending.pop_front();
+            }
+        }
+        const int slot = wv.slot, S = wv.S, n = wv.n_items;
+        const Model& model = *rt.models[wv.segs[0].t->model];
+        auto t_host0 = std::chrono::steady_clock::now();
+        // stage into pinned memory
+        for (const Segment& sg : wv.segs) {
+            memcpy(rt.h_ids[slot] + static_cast<size_t>(sg.wave_off) * S,
+                   sg.t->ids.data() + static_cast<size_t>(sg.ticket_off) * S, static_cast<size_t>(sg.count) * S * 4);
+            memcpy(rt.h_lens[slot] + sg.wave_off, sg.t->lens.data() + sg.ticket_off, static_cast<size_t>(sg.count) * 4);
+        }
+        auto t_host1 = std::chrono::steady_clock::now();
+        SCHED_TRY(cudaSetDevice(root.id));
+        SCHED_TRY(cudaEventRecord(rt.ev_t0[slot], rt.s_in));
+        SCHED_TRY(cudaMemcpyAsync(rt.d_ids_stage[slot], rt.h_ids[slot], static_cast<size_t>(n) * S * 4,
+                                  cudaMemcpyHostToDevice, rt.s_in));
+        SCHED_TRY(cudaMemcpyAsync(rt.d_lens_stage[slot], rt.h_lens[slot], static_cast<size_t>(n) * 4,
+                                  cudaMemcpyHostToDevice, rt.s_in));
+        // contiguous item ranges, as even as possible
+        ScatterPlan plan{};
+        plan.n_shards = G;
+        plan.S = S;
+        const int per = (n + G - 1) / G;
+        uint64_t peer_bytes = 0;
+        for (int g = 0; g < G; ++g) {
+            const int b0 = std::min(n, g * per), b1 = std::min(n, (g + 1) * per);
+            plan.dst_ids[g] = rt.devs[g]->ids_in[slot];
+            plan.dst_lens[g] = rt.devs[g]->lens_in[slot];
+            plan.item_begin[g] = b0;
+            plan.item_count[g] = b1 - b0;
+            if (g != 0) peer_bytes += static_cast<uint64_t>(b1 - b0) * (S * 4 + 4 + HIDDEN * 4);
+        }
+        SCHED_TRY(launch_scatter(rt.d_ids_stage[slot], rt.d_lens_stage[slot], plan, rt.s_in));
+        SCHED_TRY(cudaEventRecord(rt.ev_scatter[slot], rt.s_in));
+        uint64_t launches = 1;
+        for (int g = 0; g < G; ++g) {
+            if (plan.item_count[g] == 0) continue;
+            Dev& d = *rt.devs[g];
+            std::lock_guard<std::mutex> dl(d.mu);
+            SCHED_TRY(cudaSetDevice(d.id));
+            SCHED_TRY(cudaStreamWaitEvent(d.compute, rt.ev_scatter[slot], 0));
+            float* dst = rt.d_out_gather[slot] + static_cast<size_t>(plan.item_begin[g]) * HIDDEN;
+            int rc = forward(d, model, g, d.ids_in[slot], d.lens_in[slot], plan.item_count[g], S, dst, d.compute, -1,
+                             nullptr, &launches);
+            if (rc) {
+                fail_all(rt, t_last_error);
+                return;
+            }
+            SCHED_TRY(cudaEventRecord(d.ev_done[slot], d.compute));
+        }
+        SCHED_TRY(cudaSetDevice(root.id));
+        for (int g = 0; g < G; ++g)
+            if (plan.item_count[g] > 0) SCHED_TRY(cudaStreamWaitEvent(rt.s_out, rt.devs[g]->ev_done[slot], 0));
+        SCHED_TRY(cudaEventRecord(rt.ev_fwd_end[slot], rt.s_out));
+        SCHED_TRY(cudaMemcpyAsync(rt.h_out[slot], rt.d_out_gather[slot], static_cast<size_t>(n) * HIDDEN * 4,
+                                  cudaMemcpyDeviceToHost, rt.s_out));
+        SCHED_TRY(cudaEventRecord(rt.ev_wave[slot], rt.s_out));
+        {
+            std::lock_guard<std::mutex> sl(rt.stats_mu);
+            rt.stats.kernel_launches += launches;
+            rt.stats.h2d_bytes += static_cast<uint64_t>(n) * (S * 4 + 4);
+            rt.stats.d2h_bytes += static_cast<uint64_t>(n) * HIDDEN * 4;
+            rt.stats.peer_bytes += peer_bytes;
+            rt.stats.stage_us += std::chrono::duration<double, std::micro>(t_host1 - t_host0).count();
+        }
+        {
+            std::lock_guard<std::mutex> lk(rt.mu);
+            rt.inflight.push_back(std::move(wv));
+            rt.cv_wave.notify_one();
+        }
+    }
+}
+
+void completer_main(Runtime* rtp) {
+    Runtime& rt = *rtp;
+    cudaSetDevice(rt.devs[0]->id);
+    for (;;) {
+        Wave wv;
+        {
+            std::unique_lock<std::mutex> lk(rt.mu);
+            rt.cv_wave.wait(lk, [&] { return rt.stopping || !rt.inflight.empty(); });
+            if (rt.inflight.empty()) {
+                if (rt.stopping) return;
+                continue;
+            }
+            wv = std::move(rt.inflight.front());
+            rt.inflight.pop_front();
+        }
+        const int slot = wv.slot;
+        cudaError_t e = cudaEventSynchronize(rt.ev_wave[slot]);
+        if (e != cudaSuccess) {
+            g_poisoned.store(true);
+            fail_all(rt, std::string("wave failed: ") + cudaGetErrorString(e));
+            return;
+        }
+        float ms_in = 0, ms_fwd = 0, ms_out = 0;
+        cudaEventElapsedTime(&ms_in, rt.ev_t0[slot], rt.ev_scatter[slot]);
+        cudaEventElapsedTime(&ms_fwd, rt.ev_scatter[slot], rt.ev_fwd_end[slot]);
+        cudaEventElapsedTime(&ms_out, rt.ev_fwd_end[slot], rt.ev_wave[slot]);
+        for (const Segment& sg : wv.segs)
+            memcpy(sg.t->out + static_cast<size_t>(sg.ticket_off) * HIDDEN,
+                   rt.h_out[slot] + static_cast<size_t>(sg.wave_off) * HIDDEN, static_cast<size_t>(sg.count) * HIDDEN * 4);
+        {
+            std::lock_guard<std::mutex> sl(rt.stats_mu);
+            rt.stats.items += wv.n_items;
+            rt.stats.waves++;
+            rt.stats.h2d_scatter_us += ms_in * 1e3;
+            rt.stats.forward_us += ms_fwd * 1e3;
+            rt.stats.d2h_us += ms_out * 1e3;
+        }
+        {
+            std::lock_guard<std::mutex> lk(rt.mu);
+            for (const Segment& sg : wv.segs) {
+                if (sg.t->remaining.fetch_sub(sg.count) == sg.count) finish_ticket_locked(rt, sg.t, 0, "");
+            }
+            rt.slot_busy[slot] = false;
+            rt.cv_slot.notify_all();
+            rt.cv_done.notify_all();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ init / load
+
+int alloc_dev(Runtime& rt, Dev& d) {
+    CUDA_TRY(cudaSetDevice(d.id));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, d.id));
+    if (prop.major != 10)
+        return fail(B200RT_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", d.id, prop.major, prop.minor);
+    d.sm_count = prop.multiProcessorCount;
+    CUDA_TRY(kernels_init_device());
+    CUDA_TRY(cudaStreamCreateWithFlags(&d.compute, cudaStreamNonBlocking));
+    const size_t R = rt.cap_rows;
+    CUDA_TRY(cudaMalloc(&d.x32, R * HIDDEN * 4));
+    CUDA_TRY(cudaMalloc(&d.y32, R * HIDDEN * 4));
+    CUDA_TRY(cudaMalloc(&d.x16, R * HIDDEN * 2));
+    CUDA_TRY(cudaMalloc(&d.qkv, R * QKV_DIM * 2));
+    CUDA_TRY(cudaMalloc(&d.ctx, R * HIDDEN * 2));
+    CUDA_TRY(cudaMalloc(&d.ffn, R * 3072 * 2));
+    // padded / stale rows must stay finite (0 * NaN would leak through masked attention probabilities)
+    CUDA_TRY(cudaMemset(d.x32, 0, R * HIDDEN * 4));
+    CUDA_TRY(cudaMemset(d.y32, 0, R * HIDDEN * 4));
+    CUDA_TRY(cudaMemset(d.x16, 0, R * HIDDEN * 2));
+    CUDA_TRY(cudaMemset(d.qkv, 0, R * QKV_DIM * 2));
+    CUDA_TRY(cudaMemset(d.ctx, 0, R * HIDDEN * 2));
+    CUDA_TRY(cudaMemset(d.ffn, 0, R * 3072 * 2));
+    if (int rc = make_map_2d(&d.m_x16, d.x16, R, HIDDEN, 128)) return rc;
+    if (int rc = make_map_2d(&d.m_ctx, d.ctx, R, HIDDEN, 128)) return rc;
+    if (int rc = make_map_2d(&d.m_ffn, d.ffn, R, 3072, 128)) return rc;
+    for (int s = 0; s < NSLOT; ++s) {
+        CUDA_TRY(cudaMalloc(&d.ids_in[s], R * 4));
+        CUDA_TRY(cudaMalloc(&d.lens_in[s], R * 4));
+        CUDA_TRY(cudaMemset(d.ids_in[s], 0, R * 4));
+        CUDA_TRY(cudaEventCreateWithFlags(&d.ev_done[s], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+int rt_init(const int* devices, int n, uint32_t flags) {
+    (void)flags;
+    std::lock_guard<std::mutex> lk(g_rt_mu);
+    if (g_rt) return fail(B200RT_E_STATE, "b200rt already initialised");
+    if (g_poisoned.load()) return fail(B200RT_E_CUDA, "context poisoned by an earlier CUDA error");
+    if (n < 1 || n > ScatterPlan::MAX_SHARDS) return fail(B200RT_E_INVALID, "n_gpus must be in [1, 8], got %d", n);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(B200RT_E_CUDA, "no CUDA device available (%s); b200rt has no CPU path", cudaGetErrorString(e));
+    auto rt = std::make_unique<Runtime>();
+    if (const char* s = getenv("B200RT_WAVE_ITEMS")) rt->cap_items = std::max(1, atoi(s));
+    rt->cap_rows = ((rt->cap_items * MAX_SEQ + 127) / 128) * 128;
+    g_rt = rt.get();  // forward() and friends read capacity through g_rt
+    auto bail = [&](int rc) { g_rt = nullptr; return rc; };
+    if (int rc = load_driver_entry()) return bail(rc);
+    for (int i = 0; i < n; ++i) {
+        auto d = std::make_unique<Dev>();
+        d->id = devices ? devices[i] : i;
+        if (d->id < 0 || d->id >= count) return bail(fail(B200RT_E_INVALID, "device %d not present (%d visible)", d->id, count));
+        if (int rc = alloc_dev(*rt, *d)) return bail(rc);
+        rt->devs.push_back(std::move(d));
+    }
+    // peer access both ways between every pair (scatter writes root->peer, gather writes peer->root)
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, rt->devs[i]->id, rt->devs[j]->id);
+            if (!can) return bail(fail(B200RT_E_UNSUPPORTED, "no peer access between GPU %d and %d", rt->devs[i]->id, rt->devs[j]->id));
+            cudaSetDevice(rt->devs[i]->id);
+            cudaError_t pe = cudaDeviceEnablePeerAccess(rt->devs[j]->id, 0);
+            if (pe == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (pe != cudaSuccess) return bail(fail(B200RT_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(pe)));
+        }
+    Dev& root = *rt->devs[0];
+    if (cudaSetDevice(root.id) != cudaSuccess) return bail(fail(B200RT_E_CUDA, "cudaSetDevice(root)"));
+    const size_t wave_rows = static_cast<size_t>(rt->cap_rows) * n;
+    auto ck = [&](cudaError_t ce, const char* what) { return ce == cudaSuccess ? 0 : fail(B200RT_E_CUDA, "%s: %s", what, cudaGetErrorString(ce)); };
+    if (int rc = ck(cudaStreamCreateWithFlags(&rt->s_in, cudaStreamNonBlocking), "stream")) return bail(rc);
+    if (int rc = ck(cudaStreamCreateWithFlags(&rt->s_out, cudaStreamNonBlocking), "stream")) return bail(rc);
+    for (int s = 0; s < NSLOT; ++s) {
+        if (int rc = ck(cudaMallocHost(&rt->h_ids[s], wave_rows * 4), "cudaMallocHost ids")) return bail(rc);
+        if (int rc = ck(cudaMallocHost(&rt->h_lens[s], wave_rows * 4), "cudaMallocHost lens")) return bail(rc);
+        if (int rc = ck(cudaMallocHost(&rt->h_out[s], wave_rows * HIDDEN * 4), "cudaMallocHost out")) return bail(rc);
+        if (int rc = ck(cudaMalloc(&rt->d_ids_stage[s], wave_rows * 4), "cudaMalloc")) return bail(rc);
+        if (int rc = ck(cudaMalloc(&rt->d_lens_stage[s], wave_rows * 4), "cudaMalloc")) return bail(rc);
+        if (int rc = ck(cudaMalloc(&rt->d_out_gather[s], wave_rows * HIDDEN * 4), "cudaMalloc")) return bail(rc);
+        cudaEventCreate(&rt->ev_scatter[s]);
+        cudaEventCreate(&rt->ev_wave[s]);
+        cudaEventCreate(&rt->ev_t0[s]);
+        cudaEventCreate(&rt->ev_fwd_end[s]);
+    }
+    for (auto& d : rt->devs) {
+        cudaSetDevice(d->id);
+        if (int rc = ck(cudaDeviceSynchronize(), "device sync after init")) return bail(rc);
+    }
+    rt->dispatcher = std::thread(dispatcher_main, rt.get());
+    rt->completer = std::thread(completer_main, rt.get());
+    g_rt = rt.release();
+    return 0;
+}
+
+struct BlobCursor {
+    size_t f32 = 0, f16 = 0;
+};
+
+int model_load(const b200rt_bert_config& c, const float* blob, size_t nbytes, int* model_out) {
+    Runtime& rt = *g_rt;
+    if (c.hidden != HIDDEN || c.heads != HEADS || c.inter != 3072 || c.max_pos > MAX_SEQ || c.max_pos < 1 ||
+        c.layers < 1 || c.vocab < 1 || c.type_vocab < 1)
+        return fail(B200RT_E_UNSUPPORTED,
+                    "kernels are specialised for hidden=768 heads=12 inter=3072 max_pos<=512 (got %d/%d/%d/%d)", c.hidden,
+                    c.heads, c.inter, c.max_pos);
+    const size_t H = HIDDEN, I = 3072;
+    const size_t emb = (static_cast<size_t>(c.vocab) + c.max_pos + c.type_vocab) * H + 2 * H;
+    const size_t per_layer_w = 3 * H * H + H * H + I * H + H * I;
+    const size_t per_layer_p = 3 * H + H + 2 * H + I + H + 2 * H;
+    const size_t total = emb + static_cast<size_t>(c.layers) * (per_layer_w + per_layer_p);
+    if (nbytes != total * 4) return fail(B200RT_E_INVALID, "weight blob is %zu bytes, geometry needs %zu", nbytes, total * 4);
+
+    auto m = std::make_unique<Model>();
+    m->cfg = c;
+    m->f32_elems = emb + static_cast<size_t>(c.layers) * per_layer_p;
+    m->f16_elems = static_cast<size_t>(c.layers) * per_layer_w;
+    m->per_dev.resize(rt.devs.size());
+
+    // root: upload the fp32 blob once, carve fp32 params / convert GEMM weights to fp16 on the GPU
+    Dev& root = *rt.devs[0];
+    std::lock_guard<std::mutex> dl(root.mu);
+    CUDA_TRY(cudaSetDevice(root.id));
+    float* d_blob = nullptr;
+    CUDA_TRY(cudaMalloc(&d_blob, nbytes));
+    CUDA_TRY(cudaMemcpy(d_blob, blob, nbytes, cudaMemcpyHostToDevice));
+    for (size_t g = 0; g < rt.devs.size(); ++g) {
+        CUDA_TRY(cudaSetDevice(rt.devs[g]->id));
+        CUDA_TRY(cudaMalloc(&m->per_dev[g].f32_arena, m->f32_elems * 4));
+        CUDA_TRY(cudaMalloc(&m->per_dev[g].f16_arena, m->f16_elems * 2));
+    }
+    CUDA_TRY(cudaSetDevice(root.id));
+    DevWeights& rw = m->per_dev[0];
+    {
+        size_t src = 0, o32 = 0, o16 = 0;
+        auto take32 = [&](size_t n) -> cudaError_t {
+            cudaError_t e = cudaMemcpyAsync(rw.f32_arena + o32, d_blob + src, n * 4, cudaMemcpyDeviceToDevice, root.compute);
+            src += n; o32 += n;
+            return e;
+        };
+        auto take16 = [&](size_t n) -> cudaError_t {
+            cudaError_t e = launch_f32_to_f16(d_blob + src, rw.f16_arena + o16, n, root.compute);
+            src += n; o16 += n;
+            return e;
+        };
+        CUDA_TRY(take32(emb));
+        for (int l = 0; l < c.layers; ++l) {
+            CUDA_TRY(take16(3 * H * H)); CUDA_TRY(take32(3 * H));           // qkv.w, qkv.b
+            CUDA_TRY(take16(H * H));     CUDA_TRY(take32(H + 2 * H));       // ao.w, ao.b, ln1.g, ln1.b
+            CUDA_TRY(take16(I * H));     CUDA_TRY(take32(I));               // ff1.w, ff1.b
+            CUDA_TRY(take16(H * I));     CUDA_TRY(take32(H + 2 * H));       // ff2.w, ff2.b, ln2.g, ln2.b
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(root.compute));
+    CUDA_TRY(cudaFree(d_blob));
+    // one-time broadcast of the device-resident weights to the other replicas over NVLink
+    for (size_t g = 1; g < rt.devs.size(); ++g) {
+        CUDA_TRY(cudaMemcpyPeerAsync(m->per_dev[g].f32_arena, rt.devs[g]->id, rw.f32_arena, root.id, m->f32_elems * 4, root.compute));
+        CUDA_TRY(cudaMemcpyPeerAsync(m->per_dev[g].f16_arena, rt.devs[g]->id, rw.f16_arena, root.id, m->f16_elems * 2, root.compute));
+    }
+    CUDA_TRY(cudaStreamSynchronize(root.compute));
+    // carve pointers + weight tensor maps per replica
+    for (size_t g = 0; g < rt.devs.size(); ++g) {
+        DevWeights& w = m->per_dev[g];
+        CUDA_TRY(cudaSetDevice(rt.devs[g]->id));
+        float* p = w.f32_arena;
+        __half* q = w.f16_arena;
+        w.word = p; p += static_cast<size_t>(c.vocab) * H;
+        w.pos = p;  p += static_cast<size_t>(c.max_pos) * H;
+        w.type = p; p += static_cast<size_t>(c.type_vocab) * H;
+        w.emb_g = p; p += H;
+        w.emb_b = p; p += H;
+        w.layers.resize(c.layers);
+        for (int l = 0; l < c.layers; ++l) {
+            LayerW& lw = w.layers[l];
+            lw.qkv_w = q; q += 3 * H * H;  lw.qkv_b = p; p += 3 * H;
+            lw.ao_w = q;  q += H * H;      lw.ao_b = p;  p += H;  lw.ln1_g = p; p += H;  lw.ln1_b = p; p += H;
+            lw.ff1_w = q; q += I * H;      lw.ff1_b = p; p += I;
+            lw.ff2_w = q; q += H * I;      lw.ff2_b = p; p += H;  lw.ln2_g = p; p += H;  lw.ln2_b = p; p += H;
+            if (int rc = make_map_2d(&lw.m_qkv, lw.qkv_w, 3 * H, H, 256)) return rc;
+            if (int rc = make_map_2d(&lw.m_ao, lw.ao_w, H, H, 256)) return rc;
+            if (int rc = make_map_2d(&lw.m_ff1, lw.ff1_w, I, H, 256)) return rc;
+            if (int rc = make_map_2d(&lw.m_ff2, lw.ff2_w, H, I, 256)) return rc;
+        }
+    }
+    CUDA_TRY(cudaSetDevice(root.id));
+    {
+        std::lock_guard<std::mutex> lk(rt.mu);
+        rt.models.push_back(std::move(m));
+        *model_out = static_cast<int>(rt.models.size()) - 1;
+    }
+    return 0;
+}
+
+Runtime* live_rt() {
+    if (g_poisoned.load()) {
+        fail(B200RT_E_CUDA, "context poisoned by an earlier CUDA error%s%s", g_rt && !g_rt->async_error.empty() ? ": " : "",
+             g_rt ? g_rt->async_error.c_str() : "");
+        return nullptr;
+    }
+    if (!g_rt) {
+        fail(B200RT_E_STATE, "b200rt_init has not been called");
+        return nullptr;
+    }
+    return g_rt;
+}
+
+const Model* get_model(Runtime& rt, int model) {
+    std::lock_guard<std::mutex> lk(rt.mu);
+    if (model < 0 || model >= static_cast<int>(rt.models.size())) {
+        fail(B200RT_E_INVALID, "unknown model handle %d", model);
+        return nullptr;
+    }
+    return rt.models[model].get();
+}
+
+int check_ids(const b200rt_bert_config& c, const int32_t* ids, const int32_t* lens, int n_items, int max_len) {
+    if (!ids || n_items < 1) return fail(B200RT_E_INVALID, "empty input (n_items=%d)", n_items);
+    if (max_len < 1 || max_len > c.max_pos) return fail(B200RT_E_INVALID, "max_len %d outside [1, %d]", max_len, c.max_pos);
+    for (int i = 0; i < n_items; ++i) {
+        const int L = lens ? lens[i] : max_len;
+        if (L < 1 || L > max_len) return fail(B200RT_E_INVALID, "lens[%d] = %d outside [1, %d]", i, L, max_len);
+        const int32_t* row = ids + static_cast<size_t>(i) * max_len;
+        for (int j = 0; j < L; ++j)
+            if (row[j] < 0 || row[j] >= c.vocab)
+                return fail(B200RT_E_INVALID, "ids[%d][%d] = %d outside the vocabulary [0, %d)", i, j, row[j], c.vocab);
+    }
+    return 0;
+}
+
+}  // namespace
+
+// ============================================================================================ C ABI
+
+extern "C" {
+
+int b200rt_init(int n_gpus, uint32_t flags) { return rt_init(nullptr, n_gpus, flags); }
+int b200rt_init_devices(const int* devices, int n_gpus, uint32_t flags) { return rt_init(devices, n_gpus, flags); }
+
+int b200rt_num_gpus(void) {
+    Runtime* rt = live_rt();
+    return rt ? static_cast<int>(rt->devs.size()) : B200RT_E_STATE;
+}
+
+int b200rt_wave_capacity_items(void) {
+    Runtime* rt = live_rt();
+    return rt ? rt->cap_rows / MAX_SEQ : B200RT_E_STATE;
+}
+
+int b200rt_model_load(const char* kind, const void* cfg, const void* weights, size_t nbytes, int* model_out) {
+    Runtime* rt = live_rt();
+    if (!rt) return g_poisoned.load() ? B200RT_E_CUDA : B200RT_E_STATE;
+    if (!kind || strcmp(kind, "bert") != 0) return fail(B200RT_E_UNSUPPORTED, "unknown model kind '%s' (only \"bert\")", kind ? kind : "(null)");
+    if (!cfg || !weights || !model_out) return fail(B200RT_E_INVALID, "null argument");
+    return model_load(*static_cast<const b200rt_bert_config*>(cfg), static_cast<const float*>(weights), nbytes, model_out);
+}
+
+int b200rt_submit(int model, const int32_t* ids, const int32_t* lens, int n_items, int max_len, float* out,
+                  uint64_t* ticket_out) {
+    Runtime* rt = live_rt();
+    if (!rt) return g_poisoned.load() ? B200RT_E_CUDA : B200RT_E_STATE;
+    const Model* m = get_model(*rt, model);
+    if (!m) return B200RT_E_INVALID;
+    if (!out || !ticket_out) return fail(B200RT_E_INVALID, "null out / ticket_out");
+    if (int rc = check_ids(m->cfg, ids, lens, n_items, max_len)) return rc;
+    auto t = std::make_shared<Ticket>();
+    t->model = model;
+    t->n_items = n_items;
+    t->S = max_len;
+    t->out = out;
+    t->remaining.store(n_items);
+    t->ids.assign(ids, ids + static_cast<size_t>(n_items) * max_len);
+    if (lens) t->lens.assign(lens, lens + n_items);
+    else t->lens.assign(n_items, max_len);
+    {
+        std::lock_guard<std::mutex> lk(rt->mu);
+        if (rt->stopping) return fail(B200RT_E_STATE, "runtime is shutting down");
+        t->id = rt->next_ticket++;
+        rt->tickets.emplace(t->id, t);
+        rt->pending.push_back(t);
+        *ticket_out = t->id;
+    }
+    rt->cv_submit.notify_one();
+    return 0;
+}
+
+static int reap_locked(Runtime& rt, uint64_t id, const std::shared_ptr<Ticket>& t) {
+    for (auto it = rt.finished_unclaimed.begin(); it != rt.finished_unclaimed.end(); ++it)
+        if (*it == id) { rt.finished_unclaimed.erase(it); break; }
+    rt.tickets.erase(id);
+    if (t->status != 0) return fail(t->status, "ticket %llu failed: %s", (unsigned long long)id, t->error.c_str());
+    return 0;
+}
+
+int b200rt_wait(uint64_t ticket, int timeout_ms) {
+    Runtime* rt = g_rt;
+    if (!rt) return fail(B200RT_E_STATE, "b200rt_init has not been called");
+    std::unique_lock<std::mutex> lk(rt->mu);
+    auto it = rt->tickets.find(ticket);
+    if (it == rt->tickets.end()) return fail(B200RT_E_INVALID, "unknown or already reaped ticket %llu", (unsigned long long)ticket);
+    std::shared_ptr<Ticket> t = it->second;
+    auto pred = [&] { return t->done; };
+    if (timeout_ms < 0) rt->cv_done.wait(lk, pred);
+    else if (!rt->cv_done.wait_for(lk, std::chrono::milliseconds(timeout_ms), pred)) return B200RT_TIMEOUT;
+    return reap_locked(*rt, ticket, t);
+}
+
+int b200rt_poll_any(uint64_t* ticket_out, int timeout_ms) {
+    Runtime* rt = g_rt;
+    if (!rt) return fail(B200RT_E_STATE, "b200rt_init has not been called");
+    if (!ticket_out) return fail(B200RT_E_INVALID, "null ticket_out");
+    std::unique_lock<std::mutex> lk(rt->mu);
+    auto pred = [&] { return !rt->finished_unclaimed.empty(); };
+    if (timeout_ms < 0) rt->cv_done.wait(lk, pred);
+    else if (!rt->cv_done.wait_for(lk, std::chrono::milliseconds(timeout_ms), pred)) return B200RT_TIMEOUT;
+    const uint64_t id = rt->finished_unclaimed.front();
+    auto t = rt->tickets[id];
+    *ticket_out = id;
+    return reap_locked(*rt, id, t);
+}
+
+int b200rt_embed_device(int model, int gpu, const int32_t* d_ids, const int32_t* d_lens, int n_items, int max_len,
+                        float* d_out, void* stream) {
+    Runtime* rt = live_rt();
+    if (!rt) return g_poisoned.load() ? B200RT_E_CUDA : B200RT_E_STATE;
+    const Model* m = get_model(*rt, model);
+    if (!m) return B200RT_E_INVALID;
+    if (gpu < 0 || gpu >= static_cast<int>(rt->devs.size())) return fail(B200RT_E_INVALID, "gpu index %d outside the pool", gpu);
+    if (!d_ids || !d_lens || !d_out || n_items < 1 || max_len < 1 || max_len > m->cfg.max_pos) return fail(B200RT_E_INVALID, "bad argument");
+    Dev& d = *rt->devs[gpu];
+    std::lock_guard<std::mutex> dl(d.mu);
+    CUDA_TRY(cudaSetDevice(d.id));
+    uint64_t launches = 0;
+    int rc = forward(d, *m, gpu, d_ids, d_lens, n_items, max_len, d_out, stream ? static_cast<cudaStream_t>(stream) : d.compute,
+                     -1, nullptr, &launches);
+    std::lock_guard<std::mutex> sl(rt->stats_mu);
+    rt->stats.kernel_launches += launches;
+    return rc;
+}
+
+int b200rt_device_sync(int gpu) {
+    Runtime* rt = live_rt();
+    if (!rt) return g_poisoned.load() ? B200RT_E_CUDA : B200RT_E_STATE;
+    if (gpu < 0 || gpu >= static_cast<int>(rt->devs.size())) return fail(B200RT_E_INVALID, "gpu index %d outside the pool", gpu);
+    CUDA_TRY(cudaSetDevice(rt->devs[gpu]->id));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return 0;
+}
+
+void* b200rt_alloc_pinned(size_t nbytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, nbytes) != cudaSuccess) {
+        cudaGetLastError();
+        fail(B200RT_E_NOMEM, "cudaMallocHost(%zu) failed", nbytes);
+        return nullptr;
+    }
+    return p;
+}
+void b200rt_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int b200rt_stats(b200rt_stats_t* out) {
+    Runtime* rt = g_rt;
+    if (!rt) return fail(B200RT_E_STATE, "b200rt_init has not been called");
+    if (!out) return fail(B200RT_E_INVALID, "null out");
+    std::lock_guard<std::mutex> sl(rt->stats_mu);
+    *out = rt->stats;
+    return 0;
+}
+
+const char* b200rt_last_error(void) { return t_last_error.c_str(); }
+
+void b200rt_shutdown(void) {
+    std::lock_guard<std::mutex> glk(g_rt_mu);
+    Runtime* rt = g_rt;
+    if (!rt) return;
+    {
+        std::lock_guard<std::mutex> lk(rt->mu);
+        rt->stopping = true;
+        for (auto& kv : rt->tickets) finish_ticket_locked(*rt, kv.second, B200RT_E_STATE, "runtime shut down");
+    }
+    rt->cv_submit.notify_all();
+    rt->cv_slot.notify_all();
+    rt->cv_wave.notify_all();
+    rt->cv_done.notify_all();
+    if (rt->dispatcher.joinable()) rt->dispatcher.join();
+    if (rt->completer.joinable()) rt->completer.join();
+    for (auto& d : rt->devs) {
+        cudaSetDevice(d->id);
+        cudaDeviceSynchronize();
+    }
+    for (auto& m : rt->models)
+        for (size_t g = 0; g < m->per_dev.size(); ++g) {
+            cudaSetDevice(rt->devs[g]->id);
+            cudaFree(m->per_dev[g].f32_arena);
+            cudaFree(m->per_dev[g].f16_arena);
+        }
+    for (auto& d : rt->devs) {
+        cudaSetDevice(d->id);
+        cudaFree(d->x32); cudaFree(d->y32); cudaFree(d->x16); cudaFree(d->qkv); cudaFree(d->ctx); cudaFree(d->ffn);
+        for (int s = 0; s < NSLOT; ++s) { cudaFree(d->ids_in[s]); cudaFree(d->lens_in[s]); cudaEventDestroy(d->ev_done[s]); }
+        cudaStreamDestroy(d->compute);
+    }
+    cudaSetDevice(rt->devs[0]->id);
+    for (int s = 0; s < NSLOT; ++s) {
+        cudaFreeHost(rt->h_ids[s]); cudaFreeHost(rt->h_lens[s]); cudaFreeHost(rt->h_out[s]);
+        cudaFree(rt->d_ids_stage[s]); cudaFree(rt->d_lens_stage[s]); cudaFree(rt->d_out_gather[s]);
+        cudaEventDestroy(rt->ev_scatter[s]); cudaEventDestroy(rt->ev_wave[s]); cudaEventDestroy(rt->ev_t0[s]); cudaEventDestroy(rt->ev_fwd_end[s]);
+    }
+    cudaStreamDestroy(rt->s_in);
+    cudaStreamDestroy(rt->s_out);
+    delete rt;
+    g_rt = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------ debug entry points
+
+int b200rt_debug_gemm(int epi, const uint16_t* a, const uint16_t* w, const float* bias, const float* resid, void* out,
+                      int M, int N, int K, int iters, float* ms_out) {
+    Runtime* rt = live_rt();
+    if (!rt) return g_poisoned.load() ? B200RT_E_CUDA : B200RT_E_STATE;
+    if (!a || !w || !bias || !out || M < 1 || N % 256 || K % 64 || epi < 0 || epi > 2) return fail(B200RT_E_INVALID, "bad gemm arguments");
+    Dev& d = *rt->devs[0];
+    std::lock_guard<std::mutex> dl(d.mu);
+    CUDA_TRY(cudaSetDevice(d.id));
+    const size_t Mp = (static_cast<size_t>(M) + 127) / 128 * 128;
+    __half *da = nullptr, *dw = nullptr;
+    float *db = nullptr, *dr = nullptr;
+    void* dout = nullptr;
+    const size_t out_elt = epi == 2 ? 4 : 2;
+    CUDA_TRY(cudaMalloc(&da, Mp * K * 2));
+    CUDA_TRY(cudaMemset(da, 0, Mp * K * 2));
+    CUDA_TRY(cudaMalloc(&dw, static_cast<size_t>(N) * K * 2));
+    CUDA_TRY(cudaMalloc(&db, static_cast<size_t>(N) * 4));
+    CUDA_TRY(cudaMalloc(&dout, Mp * N * out_elt));
+    CUDA_TRY(cudaMemset(dout, 0xFF, Mp * N * out_elt));
+    CUDA_TRY(cudaMemcpy(da, a, static_cast<size_t>(M) * K * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dw, w, static_cast<size_t>(N) * K * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(db, bias, static_cast<size_t>(N) * 4, cudaMemcpyHostToDevice));
+    if (epi == 2) {
+        if (!resid) return fail(B200RT_E_INVALID, "epi 2 needs resid");
+        CUDA_TRY(cudaMalloc(&dr, Mp * N * 4));
+        CUDA_TRY(cudaMemcpy(dr, resid, static_cast<size_t>(M) * N * 4, cudaMemcpyHostToDevice));
+    }
+    CUtensorMap ta, tb;
+    if (int rc = make_map_2d(&ta, da, Mp, K, 128)) return rc;
+    if (int rc = make_map_2d(&tb, dw, N, K, 256)) return rc;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    if (iters < 1) iters = 1;
+    CUDA_TRY(launch_gemm(epi, ta, tb, db, dr, dout, M, N, K, d.sm_count, d.compute));  // warm-up + result
+    CUDA_TRY(cudaEventRecord(e0, d.compute));
+    for (int i = 0; i < iters; ++i) CUDA_TRY(launch_gemm(epi, ta, tb, db, dr, dout, M, N, K, d.sm_count, d.compute));
+    CUDA_TRY(cudaEventRecord(e1, d.compute));
+    CUDA_TRY(cudaStreamSynchronize(d.compute));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms_out) *ms_out = ms / iters;
+    CUDA_TRY(cudaMemcpy(out, dout, static_cast<size_t>(M) * N * out_elt, cudaMemcpyDeviceToHost));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(da); cudaFree(dw); cudaFree(db); cudaFree(dr); cudaFree(dout);
+    return 0;
+}
+
+int b200rt_debug_attention(const uint16_t* qkv, const int32_t* lens, uint16_t* ctx, int B, int S, int iters, float* ms_out) {
+    Runtime* rt = live_rt();
+    if (!rt) return g_poisoned.load() ? B200RT_E_CUDA : B200RT_E_STATE;
+    if (!qkv || !lens || !ctx || B < 1 || S < 1 || S > MAX_SEQ) return fail(B200RT_E_INVALID, "bad attention arguments");
+    Dev& d = *rt->devs[0];
+    std::lock_guard<std::mutex> dl(d.mu);
+    CUDA_TRY(cudaSetDevice(d.id));
+    const size_t M = static_cast<size_t>(B) * S;
+    __half *dq = nullptr, *dc = nullptr;
+    int32_t* dl_ = nullptr;
+    CUDA_TRY(cudaMalloc(&dq, M * QKV_DIM * 2));
+    CUDA_TRY(cudaMalloc(&dc, M * HIDDEN * 2));
+    CUDA_TRY(cudaMalloc(&dl_, static_cast<size_t>(B) * 4));
+    CUDA_TRY(cudaMemset(dc, 0xFF, M * HIDDEN * 2));
+    CUDA_TRY(cudaMemcpy(dq, qkv, M * QKV_DIM * 2, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dl_, lens, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice));
+    CUtensorMap tq;
+    if (int rc = make_map_qkv(&tq, dq, B, S)) return rc;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    if (iters < 1) iters = 1;
+    CUDA_TRY(launch_attention(tq, dl_, dc, B, S, d.compute));
+    CUDA_TRY(cudaEventRecord(e0, d.compute));
+    for (int i = 0; i < iters; ++i) CUDA_TRY(launch_attention(tq, dl_, dc, B, S, d.compute));
+    CUDA_TRY(cudaEventRecord(e1, d.compute));
+    CUDA_TRY(cudaStreamSynchronize(d.compute));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms_out) *ms_out = ms / iters;
+    CUDA_TRY(cudaMemcpy(ctx, dc, M * HIDDEN * 2, cudaMemcpyDeviceToHost));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dq); cudaFree(dc); cudaFree(dl_);
+    return 0;
+}
+
+int b200rt_debug_hidden(int model, const int32_t* ids, const int32_t* lens, int n_items, int max_len, int n_layers,
+                        float* hidden_out) {
+    Runtime* rt = live_rt();
+    if (!rt) return g_poisoned.load() ? B200RT_E_CUDA : B200RT_E_STATE;
+    const Model* m = get_model(*rt, model);
+    if (!m) return B200RT_E_INVALID;
+    if (int rc = check_ids(m->cfg, ids, lens, n_items, max_len)) return rc;
+    if (n_layers < 0 || n_layers > m->cfg.layers || !hidden_out) return fail(B200RT_E_INVALID, "bad n_layers / hidden_out");
+    Dev& d = *rt->devs[0];
+    std::lock_guard<std::mutex> dl(d.mu);
+    CUDA_TRY(cudaSetDevice(d.id));
+    const size_t M = static_cast<size_t>(n_items) * max_len;
+    if (M > static_cast<size_t>(rt->cap_rows)) return fail(B200RT_E_INVALID, "batch exceeds wave capacity");
+    std::vector<int32_t> l(n_items, max_len);
+    if (lens) l.assign(lens, lens + n_items);
+    int32_t *dids = nullptr, *dlens = nullptr;
+    CUDA_TRY(cudaMalloc(&dids, M * 4));
+    CUDA_TRY(cudaMalloc(&dlens, static_cast<size_t>(n_items) * 4));
+    CUDA_TRY(cudaMemcpy(dids, ids, M * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dlens, l.data(), static_cast<size_t>(n_items) * 4, cudaMemcpyHostToDevice));
+    int rc = forward(d, *m, 0, dids, dlens, n_items, max_len, nullptr, d.compute, n_layers);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(d.compute));
+    CUDA_TRY(cudaMemcpy(hidden_out, d.x32, M * HIDDEN * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dids); cudaFree(dlens);
+    return 0;
+}
+
+int b200rt_debug_profile_forward(int model, int n_items, int max_len, int iters, char* names_out, size_t names_cap,
+                                 float* ms_out, int* n_out, int cap) {
+    Runtime* rt = live_rt();
+    if (!rt) return g_poisoned.load() ? B200RT_E_CUDA : B200RT_E_STATE;
+    const Model* m = get_model(*rt, model);
+    if (!m) return B200RT_E_INVALID;
+    if (!names_out || !ms_out || !n_out || n_items < 1 || max_len < 1 || max_len > m->cfg.max_pos) return fail(B200RT_E_INVALID, "bad argument");
+    Dev& d = *rt->devs[0];
+    std::lock_guard<std::mutex> dl(d.mu);
+    CUDA_TRY(cudaSetDevice(d.id));
+    const size_t M = static_cast<size_t>(n_items) * max_len;
+    if (M > static_cast<size_t>(rt->cap_rows)) return fail(B200RT_E_INVALID, "batch exceeds wave capacity");
+    std::vector<int32_t> ids(M), l(n_items, max_len);
+    uint32_t x = 12345;
+    for (auto& v : ids) { x = x * 1664525u + 1013904223u; v = 1000 + static_cast<int32_t>((x >> 8) % (m->cfg.vocab - 1000)); }
+    int32_t *dids = nullptr, *dlens = nullptr;
+    float* dout = nullptr;
+    CUDA_TRY(cudaMalloc(&dids, M * 4));
+    CUDA_TRY(cudaMalloc(&dlens, static_cast<size_t>(n_items) * 4));
+    CUDA_TRY(cudaMalloc(&dout, static_cast<size_t>(n_items) * HIDDEN * 4));
+    CUDA_TRY(cudaMemcpy(dids, ids.data(), M * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dlens, l.data(), static_cast<size_t>(n_items) * 4, cudaMemcpyHostToDevice));
+    if (iters < 1) iters = 1;
+    std::map<std::string, double> acc;
+    std::vector<std::string> order;
+    for (int it = 0; it < iters + 1; ++it) {
+        Prof prof;
+        int rc = forward(d, *m, 0, dids, dlens, n_items, max_len, dout, d.compute, -1, &prof);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(d.compute));
+        for (size_t i = 1; i < prof.evs.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, prof.evs[i - 1], prof.evs[i]);
+            if (it > 0) {
+                if (!acc.count(prof.names[i])) order.push_back(prof.names[i]);
+                acc[prof.names[i]] += ms;
+            }
+        }
+        for (auto e : prof.evs) cudaEventDestroy(e);
+    }
+    size_t off = 0;
+    int n = 0;
+    for (const auto& name : order) {
+        if (n >= cap || off + name.size() + 1 > names_cap) break;
+        memcpy(names_out + off, name.c_str(), name.size() + 1);
+        off += name.size() + 1;
+        ms_out[n++] = static_cast<float>(acc[name] / iters);
+    }
+    *n_out = n;
+    cudaFree(dids); cudaFree(dlens); cudaFree(dout);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// Internal launch interface between the engine (host C++) and the sm_100a kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+enum GemmEpilogue : int {
+    EPI_BIAS_F16 = 0,       // out fp16 = acc + bias                      (fused QKV projection)
+    EPI_BIAS_GELU_F16 = 1,  // out fp16 = gelu_erf(acc + bias)            (FFN up-projection)
+    EPI_BIAS_RES_F32 = 2,   // out fp32 = acc + bias + resid (fp32)       (attention-out / FFN down)
+};
+
+constexpr int HIDDEN = 768;
+constexpr int HEADS = 12;
+constexpr int HEAD_DIM = 64;
+constexpr int QKV_DIM = 3 * HIDDEN;
+
+// One-time per-device setup (dynamic shared memory opt-in for every kernel). Call with the device current.
+cudaError_t kernels_init_device();
+
+// C[M,N] = epi(A[M,K] . W[N,K]^T + bias).  ta: 2D map over A {K, rows>=M}, box {64,128}, 128B swizzle;
+// tb: 2D map over W {K, N}, box {64,256}, 128B swizzle.  N % 256 == 0, K % 64 == 0.
+cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid,
+                        void* out, int M, int N, int K, int sm_count, cudaStream_t stream);
+
+// Multi-head self-attention over a padded batch: qkv fp16 [B, S, 2304] (Q | K | V, head-major within each),
+// lens[B] valid keys per item, ctx fp16 [B*S, 768].  tq: 3D map over qkv {2304, S, B}, box {64,128,1}, 128B swizzle.
+cudaError_t launch_attention(const CUtensorMap& tq, const int32_t* lens, __half* ctx, int B, int S,
+                             cudaStream_t stream);
+
+// word + position + token_type(0) embedding gather, LayerNorm -> x32 (fp32 residual stream) and x16 (GEMM input)
+cudaError_t launch_embed_ln(const int32_t* ids, const float* word, const float* pos, const float* type0,
+                            const float* gamma, const float* beta, float* x32, __half* x16, int n_tokens, int S,
+                            int vocab, float eps, cudaStream_t stream);
+
+// LayerNorm over rows of y (fp32 pre-LN sum) -> x32, x16
+cudaError_t launch_ln(const float* y, const float* gamma, const float* beta, float* x32, __half* x16, int n_rows,
+                      float eps, cudaStream_t stream);
+
+// final LayerNorm of the CLS row of every item + L2 normalise; row i is stored at out + (out_row0 + i) * 768,
+// where `out` may be a peer-mapped pointer into the root GPU's gather buffer (the fused gather).
+cudaError_t launch_pool_normalize(const float* y, const float* gamma, const float* beta, float* out, int n_items,
+                                  int S, float eps, cudaStream_t stream);
+
+// fp32 -> fp16 (weight conversion at model load)
+cudaError_t launch_f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t stream);
+
+// Root-side scatter of a wave's token ids / lengths into each shard's (possibly peer) input slot.
+struct ScatterPlan {
+    static constexpr int MAX_SHARDS = 8;
+    int n_shards;
+    int S;  // padded length of every item in the wave
+    int32_t* dst_ids[MAX_SHARDS];
+    int32_t* dst_lens[MAX_SHARDS];
+    int item_begin[MAX_SHARDS];
+    int item_count[MAX_SHARDS];
+};
+cudaError_t launch_scatter(const int32_t* src_ids, const int32_t* src_lens, const ScatterPlan& plan,
+                           cudaStream_t stream);
+
+}  // namespace b200
