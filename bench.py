@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- items/s for the BGE-base embed .map() hot path on N B200s (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                          # the CPU reference arm
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W   # N > 1: one rank per GPU
+
+A "step" is one pass of the hot path over one batch of synthetic input: ITEMS_PER_STEP 512-token items
+per GPU, presented as .map() inputs of 32 items (the reference's BATCH_SIZE,
+06_gpu_and_ml/embeddings/text_embeddings_inference.py:19).  Weak scaling: every rank owns one GPU and an
+equal shard of the items; the path has no data-path collective (items are independent), so ranks only
+meet in the timing barrier.
+
+  value  : device-resident throughput -- token ids already in HBM, forwards enqueued back to back through
+           b200rt_embed_device on torch's current stream, timed with CUDA events on that stream.
+  e2e    : the same metric through the C ABI a binding uses (b200rt_submit / b200rt_wait) with HOST buffers:
+           pinned ids -> H2D -> scatter kernel -> forward -> fused gather -> D2H, copies inside the timed region.
+  roofline: dominant kernel (by summed device time inside the forward, CUDA events on the compute stream)
+           against the measured tensor peak in MEASURED_PEAKS.json.
+  cpu_baseline: the oracle's HF-transformers fp32 path on the host cores (N=1, rank 0, bounded sample).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "modal-examples_b200"))
+
+METRIC = "items/sec for BGE-base embed .map()"
+SEQ = 512
+MAP_INPUT_ITEMS = 32           # reference BATCH_SIZE
+ITEMS_PER_STEP = int(os.environ.get("BENCH_ITEMS_PER_STEP", "4096"))  # per GPU
+REF_ITEMS_PER_STEP = 8         # bounded sample for the CPU arm
+FLOPS_PER_ITEM = 96.64e9       # BASELINE.md §4 (2*m*n*k, all rows, 12 layers)
+
+# per-layer algorithmic FLOPs per item of each tensor kernel (S = 512)
+KERNEL_FLOPS = {
+    "gemm_qkv": 2 * 512 * 768 * 2304, "gemm_attn_out": 2 * 512 * 768 * 768, "gemm_ffn1_gelu": 2 * 512 * 768 * 3072,
+    "gemm_ffn2": 2 * 512 * 3072 * 768, "attention": 4 * 512 * 512 * 768,
+}
+# algorithmic HBM bytes per token of the row-wise kernels
+KERNEL_BYTES = {"embed_ln": 3072 + 3072 + 1536, "ln1": 3072 + 3072 + 1536, "ln2": 3072 + 3072 + 1536}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tflops_burst=d["bf16_tflops"], tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="MEASURED_PEAKS.json (measured)")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="B200_PROFILING.md fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.lines:
+            if not (t0 <= t <= t1):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sample inside the timed region"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+
+
+def cpu_reference_run(n_items, warm_items, threads=None):
+    """HF BertModel fp32 + CLS pool + L2 normalise on the host cores (oracle/bge_ref.py); returns items/s."""
+    import numpy as np
+    import torch
+    from oracle import bge_ref as R
+
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = R.BGE_BASE
+    flat = R.make_weights(g, 0, "hf")
+    model = R.build_hf_model(flat, g)
+    ids = R.synth_ids(max(n_items, warm_items), SEQ, 0)
+    R.forward_hf(model, ids[:warm_items])
+    t0 = time.perf_counter()
+    out = R.forward_hf(model, ids[:n_items])
+    dt = time.perf_counter() - t0
+    assert np.isfinite(out).all()
+    return n_items / dt, threads, dt, model, ids
+
+
+def main_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    import numpy as np
+    from oracle import bge_ref as R
+    import torch
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    g = R.BGE_BASE
+    model = R.build_hf_model(R.make_weights(g, 0, "hf"), g)
+    ids = R.synth_ids(REF_ITEMS_PER_STEP, SEQ, 0)
+    for _ in range(max(args.warmup, 1)):
+        R.forward_hf(model, ids)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = R.forward_hf(model, ids)
+    dt = time.perf_counter() - t0
+    assert np.isfinite(out).all()
+    value = args.steps * REF_ITEMS_PER_STEP / dt
+    sample = f"{REF_ITEMS_PER_STEP} items x {SEQ} tokens per step (bounded sample of the 1M-item workload), HF BertModel fp32, torch {threads} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "items/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"bge-base-en-v1.5 embed, {SEQ}-token synthetic items, CPU oracle port of the TEI /embed path", "seq_len": SEQ,
+                   "items_per_step": REF_ITEMS_PER_STEP},
+        "cpu_baseline": {"value": value, "unit": "items/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "items/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ our arm
+
+
+def main_ours(args):
+    import numpy as np
+    import torch
+    import b200rt
+    from oracle import bge_ref as R  # weights + synthetic inputs only (shared bit-for-bit with the oracle)
+
+    rank, local_rank, world = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback for the CUDA path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    use_dist = world > 1
+    if use_dist:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    b200rt.init(devices=[local_rank])
+    g = R.BGE_BASE
+    flat = R.make_weights(g, 0, "hf")
+    model = b200rt.EmbedModel(R.geometry_dict(g), R.pack_blob(flat, g))
+    del flat
+    cap = b200rt.wave_capacity_items()
+    n_step = ITEMS_PER_STEP
+    ids_host = R.synth_ids(n_step, SEQ, seed=rank)  # every rank embeds its own shard of the corpus
+    peaks = load_peaks()
+
+    # ---------------- value: device-resident
+    d_ids = torch.from_numpy(ids_host).cuda()
+    d_lens = torch.full((n_step,), SEQ, dtype=torch.int32, device="cuda")
+    d_out = torch.empty((n_step, 768), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def device_step():
+        for i in range(0, n_step, cap):
+            n = min(cap, n_step - i)
+            model.embed_device(0, d_ids[i:].data_ptr(), d_lens[i:].data_ptr(), n, SEQ, d_out[i:].data_ptr(), stream)
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    st0 = b200rt.stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        device_step()
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    dev_ms = e0.elapsed_time(e1)
+    st1 = b200rt.stats()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    launches = st1["kernel_launches"] - st0["kernel_launches"]
+    norms = torch.linalg.vector_norm(d_out, dim=1)
+    assert torch.allclose(norms, torch.ones_like(norms), atol=1e-3), "device path produced non-unit embeddings"
+
+    # ---------------- e2e: C ABI with host buffers (.map() inputs of 32 items from pinned memory)
+    n_inputs = n_step // MAP_INPUT_ITEMS
+    pin_ids = b200rt.PinnedBuffer((n_step, SEQ), np.int32)
+    pin_ids.array[:] = ids_host
+    pin_out = b200rt.PinnedBuffer((n_step, 768), np.float32)
+
+    def e2e_step():
+        tickets = []
+        for j in range(n_inputs):
+            s = slice(j * MAP_INPUT_ITEMS, (j + 1) * MAP_INPUT_ITEMS)
+            tickets.append(model.submit(pin_ids.array[s], None, out=pin_out.array[s]))
+        for t in tickets:
+            model.wait(t)
+
+    for _ in range(max(1, args.warmup)):
+        e2e_step()
+    barrier()
+    s0 = b200rt.stats()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    s1 = b200rt.stats()
+    e2e_out = pin_out.array.copy()
+    assert np.allclose(np.linalg.norm(e2e_out, axis=1), 1.0, atol=1e-3)
+    dev_out = d_out.cpu().numpy()
+    assert float(np.abs(dev_out - e2e_out).max()) < 1e-5, "device-resident and host-buffer paths disagree"
+
+    # ---------------- max over ranks
+    if use_dist:
+        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(t[0]), float(t[1])
+        ln = torch.tensor([launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
+        launches = int(ln[0])
+    total_items = args.steps * n_step * world
+    value = total_items / (dev_ms / 1e3)
+    e2e_value = total_items / e2e_s
+
+    roofline = None
+    cpu_baseline = None
+    if rank == 0:
+        # ---------------- roofline of the dominant kernel (device events between launches, compute stream)
+        prof = model.profile_forward(cap, SEQ, iters=3)
+        top = max((k for k in prof if k in KERNEL_FLOPS), key=lambda k: prof[k])
+        n_launch = g.layers
+        achieved = KERNEL_FLOPS[top] * cap * n_launch / (prof[top] / 1e3) / 1e12
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get(top)
+        total_ms = sum(prof.values())
+        roofline = {
+            "bound": "tensor", "kernel": top, "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["tflops_sustained"], "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16/fp16 dense",
+            "launch_ms": prof[top] / n_launch, "share_of_forward": prof[top] / total_ms,
+            "forward": {"items_per_s_per_gpu": value / world, "tflops": value / world * FLOPS_PER_ITEM / 1e12,
+                        "frac_of_tensor_peak": value / world * FLOPS_PER_ITEM / 1e12 / peaks["tflops_sustained"]},
+            "per_kernel_ms": prof,
+            "hbm_kernels": {k: {"GBps": KERNEL_BYTES[k] * cap * SEQ * (n_launch if k != "embed_ln" else 1) / (prof[k] / 1e3) / 1e9,
+                                "frac": KERNEL_BYTES[k] * cap * SEQ * (n_launch if k != "embed_ln" else 1) / (prof[k] / 1e3) / 1e9 / peaks["hbm_gbs"]}
+                            for k in KERNEL_BYTES if k in prof},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, threads, dt, _, _ = cpu_reference_run(n_items=16, warm_items=4)
+            cpu_baseline = {"value": v, "unit": "items/s", "cores": threads, "kind": "port",
+                            "sample": f"16 items x {SEQ} tokens after a 4-item warm-up ({dt:.1f} s), HF BertModel fp32 (oracle), torch {threads} threads"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "items/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"06_gpu_and_ml/embeddings: BGE-base-en-v1.5 embed, synthetic {SEQ}-token items, .map() inputs of {MAP_INPUT_ITEMS}",
+                       "seq_len": SEQ, "items_per_step_per_gpu": n_step, "map_input_items": MAP_INPUT_ITEMS, "device_batch_items": cap,
+                       "weights": "HF default init, numpy default_rng(0), shared with the oracle", "parallelism": f"replicas x{world} (no data-path collective)",
+                       "l2": "per-step working set (218 MB fp16 weights + ~1.3 GB activations) exceeds the 126 MB L2; no explicit flush",
+                       "precision": "fp16 tensor-core operands, fp32 accumulate, fp32 residual/LayerNorm/softmax"},
+            "e2e": {"value": e2e_value, "unit": "items/s", "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) // args.steps,
+                    "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // args.steps, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "api": "b200rt_submit/b200rt_wait (C ABI, pinned host buffers)"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        }
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    pin_ids.free()
+    pin_out.free()
+    b200rt.shutdown()
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+    sys.exit(main_reference(args) if args.impl == "reference" else main_ours(args))
+
+
+if __name__ == "__main__":
+    main()

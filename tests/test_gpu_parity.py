@@ -1,0 +1,183 @@
+"""GPU (`-m gpu`, under gpurun): parity of the CUDA path, called through the C ABI, against the oracle
+(numpy restatement / HF BertModel on the host) and the committed golden vectors; size-independent
+properties at BASELINE.json's full shapes; error behaviour.  Bars: fp16 tensor-core GEMMs with fp32
+accumulation => per-item rel-L2 <= 1e-3 vs the fp32 oracle; exact for integer plumbing."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bge_ref as R
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-3  # north_star: "within 1e-3 relative for floating-point embeddings"
+
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+mg = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(mg)
+
+
+@pytest.fixture(scope="module")
+def rt():
+    import b200rt
+
+    b200rt.init(devices=[0])
+    yield b200rt
+    b200rt.shutdown()
+
+
+_models = {}
+
+
+def get_model(rt, layers, style, seed):
+    key = (layers, style, seed)
+    if key not in _models:
+        g = R.BertGeometry(layers=layers)
+        flat = R.make_weights(g, seed, style)
+        _models[key] = (g, flat, rt.EmbedModel(R.geometry_dict(g), R.pack_blob(flat, g)))
+    return _models[key]
+
+
+def ref_gemm(a16, w16, bias, epi, resid=None):
+    from scipy.special import erf
+
+    acc = a16.astype(np.float32) @ w16.astype(np.float32).T + bias
+    if epi == 1:
+        a64 = acc.astype(np.float64)
+        acc = (a64 * 0.5 * (1.0 + erf(a64 / np.sqrt(2.0)))).astype(np.float32)
+    if epi == 2:
+        acc = acc + resid
+    return acc
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(128, 256, 64, 0), (384, 768, 768, 0), (384, 768, 768, 1), (384, 768, 768, 2),
+                                       (1000, 768, 3072, 2), (4133, 3072, 768, 1), (148 * 128 + 5, 2304, 768, 0)])
+def test_gemm_kernel_vs_numpy(rt, M, N, K, epi):
+    rng = np.random.default_rng(M + N + K + epi)
+    a = rng.standard_normal((M, K)).astype(np.float16)
+    w = (rng.standard_normal((N, K)) * 0.05).astype(np.float16)
+    bias = rng.standard_normal(N).astype(np.float32)
+    resid = rng.standard_normal((M, N)).astype(np.float32) if epi == 2 else None
+    out, _ = rt.debug_gemm(epi, a, w, bias, resid)
+    ref = ref_gemm(a, w, bias, epi, resid)
+    # fp16 output rounding (2^-11 relative) dominates for epi 0/1; fp32 accumulation-order noise for epi 2
+    tol = (2e-3 * np.abs(ref) + 2e-3) if epi != 2 else (1e-4 * np.abs(ref) + 1e-4)
+    assert (np.abs(out.astype(np.float32) - ref) <= tol).all()
+
+
+@pytest.mark.parametrize("B,S,lens", [(1, 128, [128]), (2, 512, [512, 512]), (3, 300, [300, 17, 129]), (4, 512, [512, 1, 128, 385]),
+                                      (2, 7, [7, 3]), (1, 1, [1])])
+def test_attention_kernel_vs_numpy(rt, B, S, lens):
+    rng = np.random.default_rng(B * 1000 + S)
+    qkv = (rng.standard_normal((B * S, 2304)) * 2.0).astype(np.float16)
+    ctx, _ = rt.debug_attention(qkv, np.array(lens, np.int32), B, S)
+    q = qkv.astype(np.float64).reshape(B, S, 3, 12, 64)
+    qq, kk, vv = (q[:, :, j].transpose(0, 2, 1, 3) for j in range(3))
+    s = (qq @ kk.transpose(0, 1, 3, 2)) * 0.125
+    s = np.where((np.arange(S)[None, :] >= np.array(lens)[:, None])[:, None, None, :], -np.inf, s)
+    e = np.exp(s - s.max(-1, keepdims=True))
+    ref = ((e / e.sum(-1, keepdims=True)) @ vv).transpose(0, 2, 1, 3).reshape(B * S, 768)
+    got = ctx.astype(np.float64)
+    assert np.isfinite(got).all(), "padded query rows must stay finite"
+    assert (np.abs(got - ref) <= 4e-3 * np.abs(ref) + 4e-3).all()  # P and ctx are rounded to fp16
+
+
+def test_hidden_states_layer_by_layer(rt):
+    g, flat, model = get_model(rt, 2, "trained", 3)
+    ids, lens = R.synth_ragged(3, 200, seed=5, min_len=3)
+    _, hidden = R.forward_np(flat, ids, lens, g, dtype=np.float64, return_hidden=True)
+    for L in range(3):
+        h = model.debug_hidden(ids, lens, L)
+        for i, n in enumerate(lens):
+            d = h[i, :n] - hidden[L][i, :n]
+            rel = np.sqrt((d ** 2).sum()) / np.sqrt((hidden[L][i, :n] ** 2).sum())
+            assert rel < (1e-6 if L == 0 else REL_TOL), (L, i, rel)  # embedding+LN is pure fp32
+
+
+@pytest.mark.parametrize("case", ["A", "B", "C", "D", "E"])
+def test_embeddings_vs_golden(rt, golden, case):
+    layers, style, wseed, spec = mg.CASES[case]
+    g, flat, model = get_model(rt, layers, style, wseed)
+    ids, lens = mg.case_inputs(spec)
+    emb = model.embed(ids, lens)
+    rel = R.rel_l2(emb, golden[f"{case}_emb"])
+    assert rel.max() <= REL_TOL, rel
+    assert np.allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-5)
+
+
+def test_embeddings_vs_hf_oracle_full_shape(rt):
+    """BASELINE shape: 512-token items, 12 layers, against HF BertModel fp32 run on this box's CPU."""
+    import torch
+
+    torch.set_num_threads(min(32, os.cpu_count() or 8))
+    g, flat, model = get_model(rt, 12, "hf", 0)
+    hf = R.build_hf_model(flat, g)
+    ids = R.synth_ids(4, 512, 123)
+    assert R.rel_l2(model.embed(ids), R.forward_hf(hf, ids)).max() <= REL_TOL
+    ids2, lens2 = R.synth_ragged(6, 512, seed=77, min_len=1)
+    assert R.rel_l2(model.embed(ids2, lens2), R.forward_hf(hf, ids2, lens2)).max() <= REL_TOL
+
+
+def test_size_independent_properties_at_full_size(rt):
+    """No oracle at this size (2 waves of 512-token items): unit norm, padding independence, batch-composition
+    independence, determinism, order preservation."""
+    g, flat, model = get_model(rt, 12, "hf", 0)
+    n = rt.wave_capacity_items() * 2 + 3
+    ids = R.synth_ids(n, 512, 7)
+    a = model.embed(ids)
+    assert a.shape == (n, 768) and np.isfinite(a).all()
+    assert np.allclose(np.linalg.norm(a, axis=1), 1.0, atol=1e-5)
+    b = model.embed(ids)
+    assert np.array_equal(a, b), "same input, same wave layout => bitwise identical"
+    perm = np.random.default_rng(0).permutation(n)
+    c = model.embed(ids[perm])
+    assert R.rel_l2(c, a[perm]).max() < 1e-5, "an item's embedding must not depend on its batch neighbours"
+    solo = model.embed(ids[5:6])
+    assert R.rel_l2(solo, a[5:6]).max() < 1e-5
+    # garbage past the length must not leak
+    ids2, lens2 = R.synth_ragged(8, 512, seed=3, min_len=5)
+    d = model.embed(ids2, lens2)
+    ids3 = ids2.copy()
+    for i, L in enumerate(lens2):
+        ids3[i, L:] = 5000 + i
+    assert np.array_equal(model.embed(ids3, lens2), d)
+
+
+def test_scheduler_ordered_and_unordered_completion(rt):
+    g, flat, model = get_model(rt, 2, "trained", 3)
+    rng = np.random.default_rng(0)
+    inputs = []
+    for i in range(24):
+        S = int(rng.choice([16, 64, 512]))
+        ids, lens = R.synth_ragged(int(rng.integers(1, 40)), S, seed=200 + i)
+        inputs.append((ids, lens))
+    solo = [model.embed(i, l) for i, l in inputs]
+    tickets = [model.submit(i, l, tag=k) for k, (i, l) in enumerate(inputs)]
+    got = {}
+    for _ in range(10):  # order_outputs=False style
+        t = model.poll_any(60_000)
+        assert t is not None
+        got[t.tag] = t.out
+    for t in tickets:
+        if t.tag not in got:
+            got[t.tag] = model.wait(t, 60_000)
+    for k in range(len(inputs)):
+        assert R.rel_l2(got[k], solo[k]).max() < 1e-5
+    st = rt.stats()
+    assert st["kernel_launches"] > 0 and st["h2d_bytes"] > 0 and st["d2h_bytes"] > 0
+
+
+def test_error_behaviour(rt):
+    g, flat, model = get_model(rt, 2, "trained", 3)
+    with pytest.raises(rt.B200RTError) as e:
+        model.submit(np.full((1, 8), 30522, np.int32))  # id == vocab
+    assert e.value.code == rt.E_INVALID
+    with pytest.raises(rt.B200RTError):
+        model.submit(np.zeros((1, 513), np.int32))  # longer than max_pos
+    with pytest.raises(rt.B200RTError):
+        model.submit(np.zeros((2, 8), np.int32), lens=np.array([0, 8], np.int32))  # empty item
+    with pytest.raises(rt.B200RTError):
+        rt.EmbedModel(dict(R.geometry_dict(g), hidden=1024), R.pack_blob(flat, g))  # unsupported geometry
+    assert model.embed(np.full((1, 1), 101, np.int32)).shape == (1, 768)  # minimum size still works
