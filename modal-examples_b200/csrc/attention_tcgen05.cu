@@ -1,17 +1,21 @@
 // Multi-head self-attention for S <= 512, d = 64, on tcgen05 (sm_100a).
 //
 // One CTA per (item, head); it keeps that head's K and V (<= 512 x 64 fp16 each) resident in shared
-// memory and walks the item's 128-row query tiles (Q double-buffered by TMA).
+// memory and walks the item's 128-row query tiles (Q double-buffered by TMA).  Per query tile:
 //
-//   S_j = Q . K_j^T   for every 128-key block j: 128x128 fp32 in TMEM columns [128j, 128j+128)
-//   softmax warps (thread = query row) read S_j once, take the block max m_j, write
-//   P_j = exp2((S_j - m_j) * scale*log2e) as fp16 into a 128B-swizzled smem tile, keep l_j = sum(P_j)
-//   O_j = P_j . V_j   accumulates into TMEM columns [128j, 128j+64) (S_j is dead by then)
-//   epilogue: O = sum_j w_j O_j / sum_j w_j l_j with w_j = exp2((m_j - max_j m_j) * scale*log2e)
+//   S_j  = Q . K_j^T        one tcgen05.mma chain per 128-key block j -> TMEM columns [128j, 128j+128)
+//   the scores are consumed in 64-key SUB-blocks sb = 2j+g by two softmax warpgroups (g = 0/1,
+//   thread = query row): one pass over 64 TMEM columns held in registers -> sub-block max m_sb,
+//   P_sb = exp2((S - m_sb) * scale*log2e) as fp16 into a 128B-swizzled smem tile (3-deep ring),
+//   l_sb = sum(P_sb)
+//   O_sb = P_sb . V_sb      accumulates into TMEM columns [64sb, 64sb+64)  (S_sb is dead by then)
+//   epilogue: O = sum_sb w_sb O_sb / sum_sb w_sb l_sb,  w_sb = exp2((m_sb - max m) * scale*log2e);
+//   thread (row, g) combines d-columns [32g, 32g+32) from all sub-blocks; (m, l) pairs are exchanged
+//   through 8 KB of shared memory.
 //
-// Because every block keeps its own (m_j, l_j, O_j) there is no running-max rescale of an
-// accumulator in TMEM and no second pass over the scores.  Keys >= len are masked to -inf before
-// the max (exactly P = 0, matching HF's additive -inf mask); key blocks wholly past len are skipped.
+// Every sub-block keeps its own (m, l, O): no running-max rescale of a TMEM accumulator and no
+// second pass over the scores.  Keys >= len are masked to -inf before the max (exactly P = 0, matching
+// HF's additive -inf mask); sub-blocks wholly past len are skipped.
 //
 // Restates BertSelfAttention.forward (HF modeling_bert.py:143-207) for the TEI /embed path the
 // reference calls at 06_gpu_and_ml/embeddings/text_embeddings_inference.py:100.
@@ -21,18 +25,23 @@
 namespace b200 {
 namespace attn {
 
-constexpr int QT = 128;     // query rows per tile
-constexpr int KB = 128;     // keys per block
+constexpr int QT = 128;      // query rows per tile
+constexpr int KB = 128;      // keys per S block (one MMA chain)
+constexpr int SB = 64;       // keys per softmax / PV sub-block
 constexpr int D = HEAD_DIM;  // 64
-constexpr int MAX_KB = 4;   // S <= 512
+constexpr int MAX_KB = 4;    // S <= 512
+constexpr int MAX_SB = 8;
+constexpr int PRING = 3;
 constexpr int TILE_BYTES = 128 * D * 2;  // 16 KB: 128 rows x 128 B
-constexpr int OFF_Q = 0;                          // 2 x 16 KB
-constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;     // 4 x 16 KB
+constexpr int OFF_Q = 0;                            // 2 x 16 KB
+constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;       // 4 x 16 KB
 constexpr int OFF_V = OFF_K + MAX_KB * TILE_BYTES;  // 4 x 16 KB
-constexpr int OFF_P = OFF_V + MAX_KB * TILE_BYTES;  // 2 x 32 KB
-constexpr int OFF_BAR = OFF_P + 2 * 2 * TILE_BYTES;
+constexpr int OFF_P = OFF_V + MAX_KB * TILE_BYTES;  // 3 x 16 KB
+constexpr int OFF_ML = OFF_P + PRING * TILE_BYTES;  // float2 [MAX_SB][128] = 8 KB
+constexpr int OFF_BAR = OFF_ML + MAX_SB * QT * 8;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_SOFTMAX_THREADS = 256;
+constexpr int NUM_THREADS = 128 + NUM_SOFTMAX_THREADS;
 
 // softmax_scale * log2(e) with softmax_scale = 1/sqrt(64)
 constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;
@@ -48,11 +57,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
     uint64_t* q_full = bars + 2;    // [2]
     uint64_t* q_empty = bars + 4;   // [2]
     uint64_t* s_full = bars + 6;    // [4]
-    uint64_t* p_full = bars + 10;   // [2]
-    uint64_t* p_empty = bars + 12;  // [2]
-    uint64_t* o_full = bars + 14;
-    uint64_t* tmem_free = bars + 15;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* p_full = bars + 10;   // [3]
+    uint64_t* p_empty = bars + 13;  // [3]
+    uint64_t* o_full = bars + 16;
+    uint64_t* tmem_free = bars + 17;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+    float2* ml = reinterpret_cast<float2*>(smem + OFF_ML);  // [MAX_SB][128]
 
     const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
     const int lane = lane_id();
@@ -61,7 +71,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
     int len = lens[b];
     len = len < 1 ? 1 : (len > S ? S : len);
     const int nq = (S + QT - 1) / QT;
-    const int nkb = (len + KB - 1) / KB;
+    const int nsb = (len + SB - 1) / SB;   // valid 64-key sub-blocks
+    const int nkb = (nsb + 1) / 2;         // 128-key blocks holding them
 
     if (warp == 0 && elect_one()) prefetch_tmap(&tq);
     if (warp == 1 && elect_one()) {
@@ -70,12 +81,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
         for (int i = 0; i < 2; ++i) {
             mbar_init(&q_full[i], 1);
             mbar_init(&q_empty[i], 1);
+        }
+        for (int i = 0; i < PRING; ++i) {
             mbar_init(&p_full[i], 128);
             mbar_init(&p_empty[i], 1);
         }
         for (int i = 0; i < MAX_KB; ++i) mbar_init(&s_full[i], 1);
         mbar_init(o_full, 1);
-        mbar_init(tmem_free, 128);
+        mbar_init(tmem_free, NUM_SOFTMAX_THREADS);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -105,8 +118,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
     } else if (warp == 1) {
         if (elect_one()) {
             // ------------------------------------------------------------ MMA issuer
-            constexpr uint32_t idesc_s = make_idesc_f16(QT, KB);         // 128 x 128, both K-major
-            constexpr uint32_t idesc_o = make_idesc_f16(QT, D, 0, 1);    // 128 x 64, B (= V) MN-major
+            constexpr uint32_t idesc_s = make_idesc_f16(QT, KB);       // 128 x 128, both K-major
+            constexpr uint32_t idesc_o = make_idesc_f16(QT, D, 0, 1);  // 128 x 64, B (= V) MN-major
             const uint32_t k_addr = smem_u32(smem + OFF_K);
             const uint32_t v_addr = smem_u32(smem + OFF_V);
             const uint32_t p_addr = smem_u32(smem + OFF_P);
@@ -128,15 +141,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
                 }
                 umma_commit(&q_empty[slot]);
                 if (qt == 0) mbar_wait(v_full, 0);
-                for (int j = 0; j < nkb; ++j) {
-                    const uint32_t pb = pcount & 1;
-                    mbar_wait(&p_full[pb], (pcount >> 1) & 1);
+                for (int sb = 0; sb < nsb; ++sb) {
+                    const uint32_t pb = pcount % PRING;
+                    mbar_wait(&p_full[pb], (pcount / PRING) & 1);
                     tc_fence_after();
 #pragma unroll
-                    for (int kk = 0; kk < KB / 16; ++kk) {
-                        const uint32_t a = p_addr + pb * (2 * TILE_BYTES) + (kk >> 2) * TILE_BYTES + (kk & 3) * 32;
-                        const uint32_t bv = v_addr + j * TILE_BYTES + kk * (16 * 128);
-                        umma_f16_ss(tmem_base + j * KB, make_sw128_desc(a), make_sw128_desc(bv), idesc_o, kk != 0);
+                    for (int kk = 0; kk < SB / 16; ++kk) {
+                        const uint32_t a = p_addr + pb * TILE_BYTES + kk * 32;
+                        const uint32_t bv = v_addr + (sb * SB + kk * 16) * 128;  // key row -> 128 B
+                        umma_f16_ss(tmem_base + sb * SB, make_sw128_desc(a), make_sw128_desc(bv), idesc_o, kk != 0);
                     }
                     umma_commit(&p_empty[pb]);
                     ++pcount;
@@ -146,112 +159,98 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
         }
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- softmax + epilogue warps
-        const int ew = warp - 4;
-        const int r = ew * 32 + lane;  // query row within the tile == TMEM lane
-        const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
+        const int e = warp - 4;
+        const int g = e >> 2;                 // which 64-key half of every 128-key block
+        const int r = (e & 3) * 32 + lane;    // query row within the tile == TMEM lane
+        const uint32_t lane_base = static_cast<uint32_t>((e & 3) * 32) << 16;
         uint8_t* p_base = smem + OFF_P;
-        uint32_t pcount = 0;
         for (int qt = 0; qt < nq; ++qt) {
-            float m_blk[MAX_KB], l_blk[MAX_KB];
-#pragma unroll
-            for (int j = 0; j < MAX_KB; ++j) {
-                m_blk[j] = -INFINITY;
-                l_blk[j] = 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < MAX_KB; ++j) {
-                if (j < nkb) {
-                    mbar_wait(&s_full[j], qt & 1);
-                    tc_fence_after();
-                    const uint32_t pb = pcount & 1;
-                    const int valid = len - j * KB;  // keys [0, valid) of this block are real (>= 1)
-                    // pass 1: block max over the 128 scores of this row
-                    float mx = -INFINITY;
 #pragma unroll 1
-                    for (int c = 0; c < KB / 32; ++c) {
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(tmem_base + lane_base + j * KB + c * 32, v);
-                        tmem_ld_wait();
+            for (int j = 0; j < nkb; ++j) {
+                const int sb = 2 * j + g;
+                if (sb >= nsb) break;
+                mbar_wait(&s_full[j], qt & 1);
+                tc_fence_after();
+                const int valid = len - sb * SB;  // keys [0, valid) of this sub-block are real (>= 1)
+                uint32_t v[64];
+                tmem_ld_32x32b_x32(tmem_base + lane_base + sb * SB, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                tmem_ld_32x32b_x32(tmem_base + lane_base + sb * SB + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                tmem_ld_wait();
+                float mx = -INFINITY;
+                if (valid >= SB) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const float s = (c * 32 + i < valid) ? __uint_as_float(v[i]) : -INFINITY;
-                            mx = fmaxf(mx, s);
-                        }
+                    for (int i = 0; i < SB; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < SB; ++i) {
+                        if (i >= valid) v[i] = __float_as_uint(-INFINITY);
+                        mx = fmaxf(mx, __uint_as_float(v[i]));
                     }
-                    const float neg_ms = -mx * kScaleLog2e;
-                    mbar_wait(&p_empty[pb], ((pcount >> 1) & 1) ^ 1);
-                    // pass 2: P = exp2(s*c - m*c), row sum, fp16 pack, swizzled smem store
-                    float lsum = 0.f;
-                    uint8_t* p_tile = p_base + pb * (2 * TILE_BYTES);
-#pragma unroll 1
-                    for (int c = 0; c < KB / 32; ++c) {
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(tmem_base + lane_base + j * KB + c * 32, v);
-                        tmem_ld_wait();
-                        uint32_t packed[16];
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const float s0 = (c * 32 + i < valid) ? __uint_as_float(v[i]) : -INFINITY;
-                            const float s1 = (c * 32 + i + 1 < valid) ? __uint_as_float(v[i + 1]) : -INFINITY;
-                            const float p0 = ex2_approx(fmaf(s0, kScaleLog2e, neg_ms));
-                            const float p1 = ex2_approx(fmaf(s1, kScaleLog2e, neg_ms));
-                            lsum += p0 + p1;
-                            packed[i >> 1] = pack_half2(p0, p1);
-                        }
-                        // keys c*32 .. c*32+31 of row r -> sub-tile (c>>1), 16B chunks ((c&1)*4 + q) ^ (r&7)
-                        uint8_t* row_ptr = p_tile + (c >> 1) * TILE_BYTES + r * 128;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int chunk = ((c & 1) * 4 + q) ^ (r & 7);
-                            *reinterpret_cast<uint4*>(row_ptr + chunk * 16) =
-                                make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-                        }
-                    }
-                    m_blk[j] = mx;
-                    l_blk[j] = lsum;
-                    tc_fence_before();          // our TMEM reads of S_j precede the MMA that overwrites it with O_j
-                    fence_proxy_async_smem();   // P_j visible to the tensor core's async-proxy reads
-                    mbar_arrive(&p_full[pb]);
-                    ++pcount;
                 }
-            }
-            // combine the per-block partial results
-            float m_all = m_blk[0];
+                const float neg_ms = -mx * kScaleLog2e;
+                // the P ring is shared by both warpgroups and is consumed in sub-block order
+                const uint32_t pidx = static_cast<uint32_t>(qt) * nsb + sb;
+                const uint32_t pb = pidx % PRING;
+                mbar_wait(&p_empty[pb], ((pidx / PRING) & 1) ^ 1);
+                float lsum = 0.f;
+                uint8_t* row_ptr = p_base + pb * TILE_BYTES + r * 128;
 #pragma unroll
-            for (int j = 1; j < MAX_KB; ++j) m_all = fmaxf(m_all, m_blk[j]);
-            float w[MAX_KB];
+                for (int q = 0; q < 8; ++q) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(v[q * 8 + 2 * i]), kScaleLog2e, neg_ms));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(v[q * 8 + 2 * i + 1]), kScaleLog2e, neg_ms));
+                        lsum += p0 + p1;
+                        pk[i] = pack_half2(p0, p1);
+                    }
+                    // keys 8q .. 8q+7 of row r -> 16-byte chunk q ^ (r & 7) of the row's 128 bytes
+                    *reinterpret_cast<uint4*>(row_ptr + ((q ^ (r & 7)) * 16)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+                ml[sb * QT + r] = make_float2(mx, lsum);
+                tc_fence_before();         // our TMEM reads of S_sb precede the MMA that overwrites it with O_sb
+                fence_proxy_async_smem();  // P_sb visible to the tensor core's async-proxy reads
+                mbar_arrive(&p_full[pb]);
+            }
+            // every (m, l) of this tile is in smem once all softmax threads are here
+            named_bar_sync(1, NUM_SOFTMAX_THREADS);
+            float m_all = -INFINITY;
+            for (int sb = 0; sb < nsb; ++sb) m_all = fmaxf(m_all, ml[sb * QT + r].x);
+            float w[MAX_SB];
             float L = 0.f;
 #pragma unroll
-            for (int j = 0; j < MAX_KB; ++j) {
-                w[j] = (j < nkb) ? ex2_approx((m_blk[j] - m_all) * kScaleLog2e) : 0.f;
-                L += w[j] * l_blk[j];
+            for (int sb = 0; sb < MAX_SB; ++sb) {
+                if (sb < nsb) {
+                    const float2 t = ml[sb * QT + r];
+                    w[sb] = ex2_approx((t.x - m_all) * kScaleLog2e);
+                    L = fmaf(w[sb], t.y, L);
+                } else {
+                    w[sb] = 0.f;
+                }
             }
             const float inv_l = 1.0f / L;
             mbar_wait(o_full, qt & 1);
             tc_fence_after();
-            float acc[D];
+            float acc[32];
 #pragma unroll
-            for (int i = 0; i < D; ++i) acc[i] = 0.f;
+            for (int i = 0; i < 32; ++i) acc[i] = 0.f;
 #pragma unroll
-            for (int j = 0; j < MAX_KB; ++j) {
-                if (j < nkb) {
+            for (int sb = 0; sb < MAX_SB; ++sb) {
+                if (sb < nsb) {
+                    uint32_t o[32];
+                    tmem_ld_32x32b_x32(tmem_base + lane_base + sb * SB + g * 32, o);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < D / 32; ++c) {
-                        uint32_t v[32];
-                        tmem_ld_32x32b_x32(tmem_base + lane_base + j * KB + c * 32, v);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) acc[c * 32 + i] = fmaf(w[j], __uint_as_float(v[i]), acc[c * 32 + i]);
-                    }
+                    for (int i = 0; i < 32; ++i) acc[i] = fmaf(w[sb], __uint_as_float(o[i]), acc[i]);
                 }
             }
             tc_fence_before();
-            mbar_arrive(tmem_free);
+            mbar_arrive(tmem_free);  // also orders our reads of `ml` before the next tile's writes
             const int q_row = qt * QT + r;
             if (q_row < S) {
-                uint4* dst = reinterpret_cast<uint4*>(ctx + (static_cast<size_t>(b) * S + q_row) * HIDDEN + h * D);
+                uint4* dst = reinterpret_cast<uint4*>(ctx + (static_cast<size_t>(b) * S + q_row) * HIDDEN + h * D + g * 32);
 #pragma unroll
-                for (int i = 0; i < D / 8; ++i) {
+                for (int i = 0; i < 4; ++i) {
                     dst[i] = make_uint4(pack_half2(acc[8 * i] * inv_l, acc[8 * i + 1] * inv_l),
                                         pack_half2(acc[8 * i + 2] * inv_l, acc[8 * i + 3] * inv_l),
                                         pack_half2(acc[8 * i + 4] * inv_l, acc[8 * i + 5] * inv_l),

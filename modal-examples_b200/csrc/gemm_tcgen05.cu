@@ -3,8 +3,8 @@
 //   A: fp16 row-major [M,K] (activations), W: fp16 row-major [N,K] (HF Linear weight, y = x W^T + b)
 //   -> both operands are K-major, the canonical UMMA "TN" case.
 //   TMA (128B swizzle) -> 4-stage smem ring -> tcgen05.mma 128x256x16 (one issuing thread) ->
-//   fp32 accumulators in TMEM, double buffered (2 x 256 columns) -> 4 epilogue warps read TMEM
-//   (tcgen05.ld 32x32b), fuse bias / erf-GELU / fp32 residual add, store to global.
+//   fp32 accumulators in TMEM, double buffered (2 x 256 columns) -> 8 epilogue warps read TMEM
+//   (tcgen05.ld 32x32b; 8 warps, two per SMSP), fuse bias / erf-GELU / fp32 residual add, store to global.
 //
 // Replaces (inside TEI, un-vendored; restated from HF modeling_bert.py): the Linear layers of
 // BertSelfAttention :143-207 (fused QKV), BertSelfOutput.dense :287-298, BertIntermediate :330-342
@@ -19,23 +19,26 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_BYTES = BN * BK * 2;          // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 48 KB
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_EPI_WARPS = 8;  // two per SMSP: warps 4..7 take columns [0,128), warps 8..11 take [128,256)
+constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
 
-// erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): 2 MUFU + ~10 FMA-pipe ops, so the FFN1
-// epilogue (128x256 elements per tile per 6144 MMA cycles) stays under the issue budget.
+// GELU(x) = x * Phi(x), Phi via erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7 on erf):
+//   a = |x|/sqrt2, t = 1/(1 + p a), q = 0.5 * poly(t) * exp(-a^2);  Phi = x >= 0 ? 1 - q : q.
+// 2 MUFU (rcp, ex2) + ~12 FMA-pipe ops per element, so the FFN1 epilogue (128x256 elements per tile)
+// stays inside the issue budget of the tile's MMA time.
 __device__ __forceinline__ float gelu_erf(float x) {
-    const float a = fabsf(x) * 0.70710678118654752f;
-    const float t = __frcp_rn(fmaf(0.3275911f, a, 1.0f));
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    p *= t;
-    const float e = ex2_approx(-a * a * 1.4426950408889634f);
-    const float erf_abs = fmaf(-p, e, 1.0f);
-    const float erf_v = copysignf(erf_abs, x);
-    return 0.5f * x * (1.0f + erf_v);
+    const float ax = fabsf(x);
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f)));
+    float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+    p = fmaf(p, t, 0.5f * 1.421413741f);
+    p = fmaf(p, t, 0.5f * -0.284496736f);
+    p = fmaf(p, t, 0.5f * 0.254829592f);
+    const float e = ex2_approx((ax * (-0.5f * 1.4426950408889634f)) * ax);
+    const float q = (p * t) * e;
+    const float phi = x >= 0.f ? 1.0f - q : q;
+    return x * phi;
 }
 
 template <int EPI>
@@ -70,7 +73,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], 4);
+            mbar_init(&tempty[s], NUM_EPI_WARPS);
         }
         fence_barrier_init();
     }
@@ -129,42 +132,63 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
     } else if (warp >= 4) {
         // -------------------------------------------------------------------- epilogue warps
-        const int ew = warp - 4;  // == warp % 4: this warp may touch TMEM lanes [32*ew, 32*ew+32)
+        const int ew = warp & 3;          // this warp may touch TMEM lanes [32*ew, 32*ew+32)
+        const int half = (warp - 4) >> 2;  // which 128 columns of the tile
+        constexpr int CHUNKS = BN / 2 / 32;  // 4 chunks of 32 columns per warp
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
-            mbar_wait(&tfull[as], aphase);
-            tc_fence_after();
             const int row = m_blk * BM + ew * 32 + lane;
             const bool row_ok = row < M;
-            const size_t row_off = static_cast<size_t>(row) * N + static_cast<size_t>(n_blk) * BN;
+            const int col0 = n_blk * BN + half * (BN / 2);
+            const size_t row_off = static_cast<size_t>(row) * N + col0;
+            float4 rq[8];  // residual of the chunk about to be processed (prefetched: it does not depend on the MMA)
+            if constexpr (EPI == EPI_BIAS_RES_F32) {
+                if (row_ok) {
+                    const float4* r4 = reinterpret_cast<const float4*>(resid + row_off);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rq[j] = r4[j];
+                }
+            }
+            mbar_wait(&tfull[as], aphase);
+            tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < CHUNKS; ++c) {
                 uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + c * 32, r);
+                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + half * (BN / 2) + c * 32, r);
+                float4 rn[8];
+                if constexpr (EPI == EPI_BIAS_RES_F32) {
+                    if (row_ok && c + 1 < CHUNKS) {
+                        const float4* r4 = reinterpret_cast<const float4*>(resid + row_off + (c + 1) * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rn[j] = r4[j];
+                    }
+                }
+                const float4* b4 = reinterpret_cast<const float4*>(bias + col0 + c * 32);
+                float4 bq[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bq[j] = __ldg(b4 + j);
                 tmem_ld_wait();
-                const float4* b4 = reinterpret_cast<const float4*>(bias + n_blk * BN + c * 32);
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 b = __ldg(b4 + j);
-                    v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + b.x;
-                    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b.y;
-                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b.z;
-                    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b.w;
+                    v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bq[j].x;
+                    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bq[j].y;
+                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bq[j].z;
+                    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bq[j].w;
                 }
                 if constexpr (EPI == EPI_BIAS_RES_F32) {
                     if (row_ok) {
-                        const float4* r4 = reinterpret_cast<const float4*>(resid + row_off + c * 32);
                         float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(out) + row_off + c * 32);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 q = r4[j];
-                            o4[j] = make_float4(v[4 * j] + q.x, v[4 * j + 1] + q.y, v[4 * j + 2] + q.z,
-                                                v[4 * j + 3] + q.w);
+                            o4[j] = make_float4(v[4 * j] + rq[j].x, v[4 * j + 1] + rq[j].y, v[4 * j + 2] + rq[j].z,
+                                                v[4 * j + 3] + rq[j].w);
                         }
                     }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) rq[j] = rn[j];
                 } else {
                     if constexpr (EPI == EPI_BIAS_GELU_F16) {
 #pragma unroll

@@ -267,7 +267,7 @@ def run_stage(name):
         print(res["traceback"], flush=True)
     res["seconds"] = time.time() - t0
     os.makedirs(OUT, exist_ok=True)
-    with open(os.path.join(OUT, f"{name}.json"), "w") as f:
+    with open(os.path.join(OUT, f"{name}{os.environ.get('BRINGUP_TAG', '')}.json"), "w") as f:
         json.dump(res, f, indent=1)
     return res["ok"]
 
@@ -284,7 +284,7 @@ def main():
     summary = {}
     for st in a.stages.split(","):
         t0 = time.time()
-        with open(os.path.join(OUT, f"{st}.log"), "w") as log:
+        with open(os.path.join(OUT, f"{st}{os.environ.get('BRINGUP_TAG', '')}.log"), "w") as log:
             try:
                 p = subprocess.run([sys.executable, os.path.abspath(__file__), "--stage", st], stdout=log, stderr=subprocess.STDOUT,
                                    timeout=a.timeout)
@@ -292,9 +292,9 @@ def main():
             except subprocess.TimeoutExpired:
                 summary[st] = {"rc": "timeout", "s": round(time.time() - t0, 1)}
         print(st, summary[st], flush=True)
-        tail = open(os.path.join(OUT, f"{st}.log")).read()[-1500:]
+        tail = open(os.path.join(OUT, f"{st}{os.environ.get('BRINGUP_TAG', '')}.log")).read()[-2500:]
         print(tail, flush=True)
-    with open(os.path.join(OUT, "summary.json"), "w") as f:
+    with open(os.path.join(OUT, f"summary{os.environ.get('BRINGUP_TAG', '')}.json"), "w") as f:
         json.dump(summary, f, indent=1)
 
 
