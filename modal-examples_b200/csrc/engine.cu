@@ -28,14 +28,9 @@
 
 namespace b200 {
 cudaError_t gemm_init_device();
-cudaError_t gemm2_init_device();
 cudaError_t attention_init_device();
-cudaError_t launch_gemm_pair(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid,
-                             void* out, int M, int N, int K, int sm_count, cudaStream_t stream);
 cudaError_t kernels_init_device() {
     cudaError_t e = gemm_init_device();
-    if (e != cudaSuccess) return e;
-    e = gemm2_init_device();
     if (e != cudaSuccess) return e;
     return attention_init_device();
 }
@@ -122,8 +117,7 @@ constexpr int MAX_SEQ = 512;
 struct LayerW {
     __half *qkv_w, *ao_w, *ff1_w, *ff2_w;
     float *qkv_b, *ao_b, *ln1_g, *ln1_b, *ff1_b, *ff2_b, *ln2_g, *ln2_b;
-    CUtensorMap m_qkv, m_ao, m_ff1, m_ff2;  // box {64,256}: single-CTA kernel
-    CUtensorMap p_qkv, p_ao, p_ff1, p_ff2;  // box {64,128}: CTA-pair kernel
+    CUtensorMap m_qkv, m_ao, m_ff1, m_ff2;  // box {64,128}: each CTA of a pair stages half of the tile's columns
 };
 
 struct DevWeights {
@@ -210,13 +204,6 @@ struct Runtime {
 
 std::mutex g_rt_mu;
 Runtime* g_rt = nullptr;
-bool g_gemm_pair = true;  // development switch (B200RT_GEMM_PAIR=0 selects the single-CTA kernel)
-
-cudaError_t do_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb1, const CUtensorMap& tb2, const float* bias,
-                    const float* resid, void* out, int M, int N, int K, int sm_count, cudaStream_t stream) {
-    return g_gemm_pair ? launch_gemm_pair(epi, ta, tb2, bias, resid, out, M, N, K, sm_count, stream)
-                       : launch_gemm(epi, ta, tb1, bias, resid, out, M, N, K, sm_count, stream);
-}
 
 // ------------------------------------------------------------------------------------------ forward
 
@@ -265,17 +252,17 @@ int forward(Dev& d, const Model& m, int dev_index, const int32_t* ids, const int
     ++nl; mark("embed_ln");
     for (int l = 0; l < L; ++l) {
         const LayerW& lw = w.layers[l];
-        CUDA_TRY(do_gemm(EPI_BIAS_F16, d.m_x16, lw.m_qkv, lw.p_qkv, lw.qkv_b, nullptr, d.qkv, M, QKV_DIM, HIDDEN, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_x16, lw.m_qkv, lw.qkv_b, nullptr, d.qkv, M, QKV_DIM, HIDDEN, d.sm_count, stream));
         ++nl; mark("gemm_qkv");
         CUDA_TRY(launch_attention(*mq, lens, d.ctx, B, S, stream));
         ++nl; mark("attention");
-        CUDA_TRY(do_gemm(EPI_BIAS_RES_F32, d.m_ctx, lw.m_ao, lw.p_ao, lw.ao_b, d.x32, d.y32, M, HIDDEN, HIDDEN, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_F32, d.m_ctx, lw.m_ao, lw.ao_b, d.x32, d.y32, M, HIDDEN, HIDDEN, d.sm_count, stream));
         ++nl; mark("gemm_attn_out");
         CUDA_TRY(launch_ln(d.y32, lw.ln1_g, lw.ln1_b, d.x32, d.x16, M, c.eps, stream));
         ++nl; mark("ln1");
-        CUDA_TRY(do_gemm(EPI_BIAS_GELU_F16, d.m_x16, lw.m_ff1, lw.p_ff1, lw.ff1_b, nullptr, d.ffn, M, c.inter, HIDDEN, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_GELU_F16, d.m_x16, lw.m_ff1, lw.ff1_b, nullptr, d.ffn, M, c.inter, HIDDEN, d.sm_count, stream));
         ++nl; mark("gemm_ffn1_gelu");
-        CUDA_TRY(do_gemm(EPI_BIAS_RES_F32, d.m_ffn, lw.m_ff2, lw.p_ff2, lw.ff2_b, d.x32, d.y32, M, HIDDEN, c.inter, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_F32, d.m_ffn, lw.m_ff2, lw.ff2_b, d.x32, d.y32, M, HIDDEN, c.inter, d.sm_count, stream));
         ++nl; mark("gemm_ffn2");
         if (!(full && l == L - 1)) {
             CUDA_TRY(launch_ln(d.y32, lw.ln2_g, lw.ln2_b, d.x32, d.x16, M, c.eps, stream));
@@ -522,7 +509,6 @@ int rt_init(const int* devices, int n, uint32_t flags) {
         return fail(B200RT_E_CUDA, "no CUDA device available (%s); b200rt has no CPU path", cudaGetErrorString(e));
     auto rt = std::make_unique<Runtime>();
     if (const char* s = getenv("B200RT_WAVE_ITEMS")) rt->cap_items = std::max(1, atoi(s));
-    if (const char* s = getenv("B200RT_GEMM_PAIR")) g_gemm_pair = atoi(s) != 0;
     rt->cap_rows = ((rt->cap_items * MAX_SEQ + 127) / 128) * 128;
     g_rt = rt.get();  // forward() and friends read capacity through g_rt
     auto bail = [&](int rc) { g_rt = nullptr; return rc; };
@@ -658,14 +644,10 @@ int model_load(const b200rt_bert_config& c, const float* blob, size_t nbytes, in
             lw.ao_w = q;  q += H * H;      lw.ao_b = p;  p += H;  lw.ln1_g = p; p += H;  lw.ln1_b = p; p += H;
             lw.ff1_w = q; q += I * H;      lw.ff1_b = p; p += I;
             lw.ff2_w = q; q += H * I;      lw.ff2_b = p; p += H;  lw.ln2_g = p; p += H;  lw.ln2_b = p; p += H;
-            if (int rc = make_map_2d(&lw.m_qkv, lw.qkv_w, 3 * H, H, 256)) return rc;
-            if (int rc = make_map_2d(&lw.m_ao, lw.ao_w, H, H, 256)) return rc;
-            if (int rc = make_map_2d(&lw.m_ff1, lw.ff1_w, I, H, 256)) return rc;
-            if (int rc = make_map_2d(&lw.m_ff2, lw.ff2_w, H, I, 256)) return rc;
-            if (int rc = make_map_2d(&lw.p_qkv, lw.qkv_w, 3 * H, H, 128)) return rc;
-            if (int rc = make_map_2d(&lw.p_ao, lw.ao_w, H, H, 128)) return rc;
-            if (int rc = make_map_2d(&lw.p_ff1, lw.ff1_w, I, H, 128)) return rc;
-            if (int rc = make_map_2d(&lw.p_ff2, lw.ff2_w, H, I, 128)) return rc;
+            if (int rc = make_map_2d(&lw.m_qkv, lw.qkv_w, 3 * H, H, 128)) return rc;
+            if (int rc = make_map_2d(&lw.m_ao, lw.ao_w, H, H, 128)) return rc;
+            if (int rc = make_map_2d(&lw.m_ff1, lw.ff1_w, I, H, 128)) return rc;
+            if (int rc = make_map_2d(&lw.m_ff2, lw.ff2_w, H, I, 128)) return rc;
         }
     }
     CUDA_TRY(cudaSetDevice(root.id));
@@ -930,17 +912,16 @@ int b200rt_debug_gemm(int epi, const uint16_t* a, const uint16_t* w, const float
         CUDA_TRY(cudaMalloc(&dr, Mp * N * 4));
         CUDA_TRY(cudaMemcpy(dr, resid, static_cast<size_t>(M) * N * 4, cudaMemcpyHostToDevice));
     }
-    CUtensorMap ta, tb, tb2;
+    CUtensorMap ta, tb;
     if (int rc = make_map_2d(&ta, da, Mp, K, 128)) return rc;
-    if (int rc = make_map_2d(&tb, dw, N, K, 256)) return rc;
-    if (int rc = make_map_2d(&tb2, dw, N, K, 128)) return rc;
+    if (int rc = make_map_2d(&tb, dw, N, K, 128)) return rc;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     if (iters < 1) iters = 1;
-    CUDA_TRY(do_gemm(epi_full, ta, tb, tb2, db, dr, dout, M, N, K, d.sm_count, d.compute));  // warm-up + result
+    CUDA_TRY(launch_gemm(epi_full, ta, tb, db, dr, dout, M, N, K, d.sm_count, d.compute));  // warm-up + result
     CUDA_TRY(cudaEventRecord(e0, d.compute));
-    for (int i = 0; i < iters; ++i) CUDA_TRY(do_gemm(epi_full, ta, tb, tb2, db, dr, dout, M, N, K, d.sm_count, d.compute));
+    for (int i = 0; i < iters; ++i) CUDA_TRY(launch_gemm(epi_full, ta, tb, db, dr, dout, M, N, K, d.sm_count, d.compute));
     CUDA_TRY(cudaEventRecord(e1, d.compute));
     CUDA_TRY(cudaStreamSynchronize(d.compute));
     float ms = 0;

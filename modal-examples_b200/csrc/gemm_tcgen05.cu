@@ -1,10 +1,17 @@
-// Persistent warp-specialised GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias)
+// CTA-pair GEMM for sm_100a (tcgen05 cta_group::2):  C[M,N] = epilogue(A[M,K] . W[N,K]^T + bias)
 //
-//   A: fp16 row-major [M,K] (activations), W: fp16 row-major [N,K] (HF Linear weight, y = x W^T + b)
-//   -> both operands are K-major, the canonical UMMA "TN" case.
-//   TMA (128B swizzle) -> 4-stage smem ring -> tcgen05.mma 128x256x16 (one issuing thread) ->
-//   fp32 accumulators in TMEM, double buffered (2 x 256 columns) -> 8 epilogue warps read TMEM
-//   (tcgen05.ld 32x32b; 8 warps, two per SMSP), fuse bias / erf-GELU / fp32 residual add, store to global.
+// A cluster of two CTAs (one TPC) owns a 256 x 256 output tile.  CTA r of the pair TMA-loads its own
+// 128 rows of A and its own 128 rows (= output columns) of W per 64-wide k-block, so each SM pulls
+// 32 KB per k-block from L2 instead of the 48 KB a lone 128x256 CTA needs (the first, single-CTA version of
+// this kernel ran into the ~10 TB/s L2->smem fill limit at ~900 TFLOP/s; see profiles/README.md).
+// The leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16); each
+// CTA's TMEM receives its 128 rows x 256 fp32 columns, double buffered (2 x 256 columns), and each
+// CTA's 8 epilogue warps drain them (bias / erf-GELU / fp32 residual add) while the next tile's MMAs run.
+//
+//   full[s]   (leader's)  : leader producer arrive.expect_tx(64 KB); both CTAs' TMA loads complete_tx on it
+//   empty[s]  (per CTA)   : tcgen05.commit multicast to both CTAs once the MMAs that read stage s retire
+//   tfull[a]  (per CTA)   : commit multicast after a tile's last MMA
+//   tempty[a] (leader's)  : 2 x 8 epilogue warps arrive (the peer's through mapa / shared::cluster)
 //
 // Replaces (inside TEI, un-vendored; restated from HF modeling_bert.py): the Linear layers of
 // BertSelfAttention :143-207 (fused QKV), BertSelfOutput.dense :287-298, BertIntermediate :330-342
@@ -15,19 +22,18 @@
 namespace b200 {
 namespace gemm {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2;          // 16 KB
-constexpr int B_BYTES = BN * BK * 2;          // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 48 KB
-constexpr int NUM_EPI_WARPS = 8;  // two per SMSP: warps 4..7 take columns [0,128), warps 8..11 take [128,256)
+constexpr int BM = 128;        // rows per CTA (256 per pair)
+constexpr int BN = 256;        // columns per pair tile; each CTA stages 128 of them
+constexpr int BK = 64, STAGES = 6;
+constexpr int A_BYTES = BM * BK * 2;            // 16 KB
+constexpr int B_BYTES = (BN / 2) * BK * 2;      // 16 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 32 KB per CTA
+constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 /*barriers*/ + 1024 /*alignment slack*/;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
 
-// GELU(x) = x * Phi(x), Phi via erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7 on erf):
-//   a = |x|/sqrt2, t = 1/(1 + p a), q = 0.5 * poly(t) * exp(-a^2);  Phi = x >= 0 ? 1 - q : q.
-// 2 MUFU (rcp, ex2) + ~12 FMA-pipe ops per element, so the FFN1 epilogue (128x256 elements per tile)
-// stays inside the issue budget of the tile's MMA time.
 __device__ __forceinline__ float gelu_erf(float x) {
+    // x * Phi(x), erf by Abramowitz-Stegun 7.1.26 (abs err <= 1.5e-7): 2 MUFU + ~12 FMA-pipe ops
     const float ax = fabsf(x);
     float t;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f)));
@@ -42,25 +48,31 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const float* __restrict__ bias, const float* __restrict__ resid, void* __restrict__ out, int M, int N,
-            int K) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const float* __restrict__ bias, const float* __restrict__ resid, void* __restrict__ out, int M, int N,
+                 int K, int dbg_mode) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-    uint64_t* full = bars;            // [STAGES] TMA -> MMA
-    uint64_t* empty = bars + STAGES;  // [STAGES] MMA -> TMA
-    uint64_t* tfull = bars + 2 * STAGES;      // [2] MMA -> epilogue
-    uint64_t* tempty = bars + 2 * STAGES + 2;  // [2] epilogue -> MMA
+    uint64_t* full = bars;                     // [STAGES]
+    uint64_t* empty = bars + STAGES;           // [STAGES]
+    uint64_t* tfull = bars + 2 * STAGES;       // [2]
+    uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
     const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
     const int lane = lane_id();
-    const int num_m = (M + BM - 1) / BM;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int pair = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+    const int num_m = (M + 2 * BM - 1) / (2 * BM);
     const int num_n = N / BN;
     const int num_tiles = num_m * num_n;
     const int kblocks = K / BK;
+    const int nstages = (dbg_mode >> 4) ? (dbg_mode >> 4) : STAGES;  // diagnostics may use a shorter ring
+    const int dmode = dbg_mode & 0xF;
 
     if (warp == 0 && elect_one()) {
         prefetch_tmap(&tma_a);
@@ -73,42 +85,49 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
-            mbar_init(&tempty[s], NUM_EPI_WARPS);
+            mbar_init(&tempty[s], 2 * NUM_EPI_WARPS);
         }
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc<512>(tmem_slot);
+    if (warp == 2) tmem_alloc_pair<512>(tmem_slot);
+    __syncwarp();
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers are initialised before anyone signals across the pair
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (elect_one()) {
-            // ---------------------------------------------------------------- TMA producer
+            // ---------------------------------------------------------------- TMA producer (both CTAs)
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
                 const int m_blk = tile / num_n, n_blk = tile % num_n;
+                const int a_row = m_blk * (2 * BM) + cta_rank * BM;
+                const int b_row = n_blk * BN + cta_rank * (BN / 2);
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-                    tma_load_2d(sa, &tma_a, &full[stage], kb * BK, m_blk * BM);
-                    tma_load_2d(sa + A_BYTES, &tma_b, &full[stage], kb * BK, n_blk * BN);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (dmode == 1) {  // diagnostics: no loads, the MMAs run on whatever is in smem
+                        if (leader) mbar_arrive(&full[stage]);
+                    } else {
+                        if (leader) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+                        tma_load_2d_pair(sa, &tma_a, &full[stage], kb * BK, a_row);
+                        tma_load_2d_pair(sa + A_BYTES, &tma_b, &full[stage], kb * BK, b_row);
+                    }
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (elect_one()) {
-            // ---------------------------------------------------------------- MMA issuer
-            constexpr uint32_t idesc = make_idesc_f16(BM, BN);
+        if (leader && elect_one()) {
+            // ---------------------------------------------------------------- MMA issuer (leader only)
+            constexpr uint32_t idesc = make_idesc_f16(2 * BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
                 mbar_wait(&tempty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * BN;
@@ -117,33 +136,35 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(smem + stage * STAGE_BYTES);
                     const uint32_t b_addr = a_addr + A_BYTES;
+                    if (dmode != 2) {  // diagnostics: mode 2 = loads only, no MMA
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        umma_f16_ss(d_tmem, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), idesc,
-                                    (kb | k) != 0);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            umma_f16_ss_pair(d_tmem, make_sw128_desc(a_addr + k * 32), make_sw128_desc(b_addr + k * 32), idesc,
+                                             (kb | k) != 0);
+                        }
                     }
-                    umma_commit(&empty[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    umma_commit_pair(&empty[stage], 0b11);
+                    if (++stage == nstages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[as]);
+                umma_commit_pair(&tfull[as], 0b11);
                 as ^= 1;
                 if (as == 0) aphase ^= 1;
             }
         }
     } else if (warp >= 4) {
-        // -------------------------------------------------------------------- epilogue warps
-        const int ew = warp & 3;          // this warp may touch TMEM lanes [32*ew, 32*ew+32)
+        // -------------------------------------------------------------------- epilogue warps (both CTAs)
+        const int ew = warp & 3;           // TMEM lanes [32*ew, 32*ew+32)
         const int half = (warp - 4) >> 2;  // which 128 columns of the tile
-        constexpr int CHUNKS = BN / 2 / 32;  // 4 chunks of 32 columns per warp
+        constexpr int CHUNKS = BN / 2 / 32;
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
             const int m_blk = tile / num_n, n_blk = tile % num_n;
-            const int row = m_blk * BM + ew * 32 + lane;
+            const int row = m_blk * (2 * BM) + cta_rank * BM + ew * 32 + lane;
             const bool row_ok = row < M;
             const int col0 = n_blk * BN + half * (BN / 2);
             const size_t row_off = static_cast<size_t>(row) * N + col0;
-            float4 rq[8];  // residual of the chunk about to be processed (prefetched: it does not depend on the MMA)
+            float4 rq[8];  // residual chunk, prefetched: it does not depend on the MMA
             if constexpr (EPI == EPI_BIAS_RES_F32) {
                 if (row_ok) {
                     const float4* r4 = reinterpret_cast<const float4*>(resid + row_off);
@@ -207,50 +228,54 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
+            if (lane == 0) mbar_arrive_cluster(&tempty[as], 0);  // the leader's barrier gates the next MMA chain
             as ^= 1;
             if (as == 0) aphase ^= 1;
         }
     }
 
+    // neither CTA may leave (or free TMEM) while its partner can still read its smem / signal its barriers
+    __syncwarp();  // re-converge the single-lane role loops before the .aligned cluster barrier
     tc_fence_before();
-    __syncthreads();
+    cluster_sync_all();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc<512>(tmem_base);
+        tmem_dealloc_pair<512>(tmem_base);
     }
 }
 
 }  // namespace gemm
 
 template <int EPI>
-static cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid,
-                              void* out, int M, int N, int K, int sm_count, cudaStream_t stream) {
-    const int tiles = ((M + gemm::BM - 1) / gemm::BM) * (N / gemm::BN);
-    const int grid = tiles < sm_count ? tiles : sm_count;
-    gemm::gemm_kernel<EPI><<<grid, gemm::NUM_THREADS, gemm::SMEM_BYTES, stream>>>(ta, tb, bias, resid, out, M, N, K);
+static cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid,
+                               void* out, int M, int N, int K, int sm_count, cudaStream_t stream, int dbg_mode) {
+    const int tiles = ((M + 2 * gemm::BM - 1) / (2 * gemm::BM)) * (N / gemm::BN);
+    int pairs = sm_count / 2;
+    if (tiles < pairs) pairs = tiles;
+    gemm::gemm_pair_kernel<EPI><<<2 * pairs, gemm::NUM_THREADS, gemm::SMEM_BYTES, stream>>>(ta, tb, bias, resid, out, M, N, K, dbg_mode);
     return cudaGetLastError();
 }
 
 cudaError_t gemm_init_device() {
     cudaError_t e;
-    e = cudaFuncSetAttribute(gemm::gemm_kernel<EPI_BIAS_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             gemm::SMEM_BYTES);
+    e = cudaFuncSetAttribute(gemm::gemm_pair_kernel<EPI_BIAS_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(gemm::gemm_kernel<EPI_BIAS_GELU_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             gemm::SMEM_BYTES);
+    e = cudaFuncSetAttribute(gemm::gemm_pair_kernel<EPI_BIAS_GELU_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(gemm::gemm_kernel<EPI_BIAS_RES_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                gemm::SMEM_BYTES);
+    return cudaFuncSetAttribute(gemm::gemm_pair_kernel<EPI_BIAS_RES_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES);
 }
 
+// tb: 2D map over W {K, N} with box {64, 128} (each CTA stages half of the tile's columns).  Bits 8+ of `epi`
+// select a diagnostic mode (1 = no TMA loads, 2 = no MMA) used only by tools/gemm_diag.py.
 cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid,
-                        void* out, int M, int N, int K, int sm_count, cudaStream_t stream) {
+                             void* out, int M, int N, int K, int sm_count, cudaStream_t stream) {
+    const int dbg_mode = epi >> 8;
+    epi &= 0xFF;
     if (N % gemm::BN != 0 || K % gemm::BK != 0 || M <= 0) return cudaErrorInvalidValue;
     switch (epi) {
-        case EPI_BIAS_F16: return launch_one<EPI_BIAS_F16>(ta, tb, bias, resid, out, M, N, K, sm_count, stream);
-        case EPI_BIAS_GELU_F16: return launch_one<EPI_BIAS_GELU_F16>(ta, tb, bias, resid, out, M, N, K, sm_count, stream);
-        case EPI_BIAS_RES_F32: return launch_one<EPI_BIAS_RES_F32>(ta, tb, bias, resid, out, M, N, K, sm_count, stream);
+        case EPI_BIAS_F16: return launch_pair<EPI_BIAS_F16>(ta, tb, bias, resid, out, M, N, K, sm_count, stream, dbg_mode);
+        case EPI_BIAS_GELU_F16: return launch_pair<EPI_BIAS_GELU_F16>(ta, tb, bias, resid, out, M, N, K, sm_count, stream, dbg_mode);
+        case EPI_BIAS_RES_F32: return launch_pair<EPI_BIAS_RES_F32>(ta, tb, bias, resid, out, M, N, K, sm_count, stream, dbg_mode);
     }
     return cudaErrorInvalidValue;
 }

@@ -21,8 +21,8 @@ constexpr int QKV_DIM = 3 * HIDDEN;
 // One-time per-device setup (dynamic shared memory opt-in for every kernel). Call with the device current.
 cudaError_t kernels_init_device();
 
-// C[M,N] = epi(A[M,K] . W[N,K]^T + bias).  ta: 2D map over A {K, rows>=M}, box {64,128}, 128B swizzle;
-// tb: 2D map over W {K, N}, box {64,256}, 128B swizzle.  N % 256 == 0, K % 64 == 0.
+// C[M,N] = epi(A[M,K] . W[N,K]^T + bias) on CTA pairs.  ta: 2D map over A {K, rows>=M}, box {64,128}, 128B swizzle;
+// tb: 2D map over W {K, N}, box {64,128}, 128B swizzle.  N % 256 == 0, K % 64 == 0.
 cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid,
                         void* out, int M, int N, int K, int sm_count, cudaStream_t stream);
 

@@ -13,15 +13,15 @@ for M, N, K, epi in [(32768, 2304, 768, 0), (32768, 768, 3072, 2), (32768, 3072,
     w = (rng.standard_normal((N, K)) * 0.05).astype(np.float16)
     bias = np.zeros(N, np.float32)
     resid = np.zeros((M, N), np.float32) if epi == 2 else None
-    for mode in (0, 1, 2):
+    for mode, nst in [(0, 0), (1, 0), (2, 0), (0, 2), (0, 3), (0, 4), (2, 2), (2, 3), (2, 4)]:
         out = np.empty((M, N), np.float32 if epi == 2 else np.float16)
         import ctypes
         ms = ctypes.c_float(0)
         lib = b200rt.load_library()
-        rc = lib.b200rt_debug_gemm(epi | (mode << 8), a.ctypes.data_as(ctypes.c_void_p), w.ctypes.data_as(ctypes.c_void_p), bias.ctypes.data_as(ctypes.c_void_p),
+        rc = lib.b200rt_debug_gemm(epi | ((mode | (nst << 4)) << 8), a.ctypes.data_as(ctypes.c_void_p), w.ctypes.data_as(ctypes.c_void_p), bias.ctypes.data_as(ctypes.c_void_p),
                                    resid.ctypes.data_as(ctypes.c_void_p) if resid is not None else None, out.ctypes.data_as(ctypes.c_void_p), M, N, K, 20, ctypes.byref(ms))
         assert rc == 0, lib.b200rt_last_error()
-        c = dict(M=M, N=N, K=K, epi=epi, mode=["normal", "mma_only", "tma_only"][mode], ms=ms.value, tflops_equiv=2.0 * M * N * K / ms.value / 1e9)
+        c = dict(M=M, N=N, K=K, epi=epi, mode=["normal", "mma_only", "tma_only"][mode], stages=nst or 6, ms=ms.value, tflops_equiv=2.0 * M * N * K / ms.value / 1e9)
         res.append(c); print(c, flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "gemm_diag.json"), "w"), indent=1)
