@@ -95,6 +95,20 @@ int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, 
     return 0;
 }
 
+// fp32 2D row-major [rows, cols] -> box {32, 128} (128-byte rows), 128B swizzle: epilogue staging tiles
+int make_map_2d_f32(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols) {
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 4};
+    cuuint32_t box[2] = {32, 128};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(B200RT_E_CUDA, "cuTensorMapEncodeTiled(f32 %llu x %llu) -> %d",
+                                       (unsigned long long)rows, (unsigned long long)cols, (int)r);
+    return 0;
+}
+
 // fp16 qkv [B, S, 2304] -> box {64, 128, 1}, 128B swizzle (rows past S are zero-filled)
 int make_map_qkv(CUtensorMap* m, const void* base, uint64_t B, uint64_t S) {
     cuuint64_t dims[3] = {QKV_DIM, S, B};
@@ -140,7 +154,9 @@ struct Dev {
     // workspace (capacity cap_rows rows)
     float *x32 = nullptr, *y32 = nullptr;
     __half *x16 = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr;
-    CUtensorMap m_x16, m_ctx, m_ffn;
+    CUtensorMap m_x16, m_ctx, m_ffn;      // fp16 [rows,*] box {64,128}: GEMM A operands (m_ffn is also FFN1's output map)
+    CUtensorMap m_qkv2d;                  // fp16 [rows,2304] box {64,128}: QKV GEMM output
+    CUtensorMap m_x32, m_y32;             // fp32 [rows,768] box {32,128}: residual in / pre-LN out of the fp32 epilogues
     std::unordered_map<int, CUtensorMap> m_qkv_by_S;
     // wave input slots (written by the root's scatter kernel, possibly over NVLink)
     int32_t* ids_in[NSLOT] = {nullptr, nullptr, nullptr};
@@ -252,17 +268,17 @@ int forward(Dev& d, const Model& m, int dev_index, const int32_t* ids, const int
     ++nl; mark("embed_ln");
     for (int l = 0; l < L; ++l) {
         const LayerW& lw = w.layers[l];
-        CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_x16, lw.m_qkv, lw.qkv_b, nullptr, d.qkv, M, QKV_DIM, HIDDEN, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_x16, lw.m_qkv, d.m_qkv2d, nullptr, lw.qkv_b, M, QKV_DIM, HIDDEN, d.sm_count, stream));
         ++nl; mark("gemm_qkv");
         CUDA_TRY(launch_attention(*mq, lens, d.ctx, B, S, stream));
         ++nl; mark("attention");
-        CUDA_TRY(launch_gemm(EPI_BIAS_RES_F32, d.m_ctx, lw.m_ao, lw.ao_b, d.x32, d.y32, M, HIDDEN, HIDDEN, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_F32, d.m_ctx, lw.m_ao, d.m_y32, &d.m_x32, lw.ao_b, M, HIDDEN, HIDDEN, d.sm_count, stream));
         ++nl; mark("gemm_attn_out");
         CUDA_TRY(launch_ln(d.y32, lw.ln1_g, lw.ln1_b, d.x32, d.x16, M, c.eps, stream));
         ++nl; mark("ln1");
-        CUDA_TRY(launch_gemm(EPI_BIAS_GELU_F16, d.m_x16, lw.m_ff1, lw.ff1_b, nullptr, d.ffn, M, c.inter, HIDDEN, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_GELU_F16, d.m_x16, lw.m_ff1, d.m_ffn, nullptr, lw.ff1_b, M, c.inter, HIDDEN, d.sm_count, stream));
         ++nl; mark("gemm_ffn1_gelu");
-        CUDA_TRY(launch_gemm(EPI_BIAS_RES_F32, d.m_ffn, lw.m_ff2, lw.ff2_b, d.x32, d.y32, M, HIDDEN, c.inter, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_F32, d.m_ffn, lw.m_ff2, d.m_y32, &d.m_x32, lw.ff2_b, M, HIDDEN, c.inter, d.sm_count, stream));
         ++nl; mark("gemm_ffn2");
         if (!(full && l == L - 1)) {
             CUDA_TRY(launch_ln(d.y32, lw.ln2_g, lw.ln2_b, d.x32, d.x16, M, c.eps, stream));
@@ -488,6 +504,9 @@ int alloc_dev(Runtime& rt, Dev& d) {
     if (int rc = make_map_2d(&d.m_x16, d.x16, R, HIDDEN, 128)) return rc;
     if (int rc = make_map_2d(&d.m_ctx, d.ctx, R, HIDDEN, 128)) return rc;
     if (int rc = make_map_2d(&d.m_ffn, d.ffn, R, 3072, 128)) return rc;
+    if (int rc = make_map_2d(&d.m_qkv2d, d.qkv, R, QKV_DIM, 128)) return rc;
+    if (int rc = make_map_2d_f32(&d.m_x32, d.x32, R, HIDDEN)) return rc;
+    if (int rc = make_map_2d_f32(&d.m_y32, d.y32, R, HIDDEN)) return rc;
     for (int s = 0; s < NSLOT; ++s) {
         CUDA_TRY(cudaMalloc(&d.ids_in[s], R * 4));
         CUDA_TRY(cudaMalloc(&d.lens_in[s], R * 4));
@@ -509,7 +528,7 @@ int rt_init(const int* devices, int n, uint32_t flags) {
         return fail(B200RT_E_CUDA, "no CUDA device available (%s); b200rt has no CPU path", cudaGetErrorString(e));
     auto rt = std::make_unique<Runtime>();
     if (const char* s = getenv("B200RT_WAVE_ITEMS")) rt->cap_items = std::max(1, atoi(s));
-    rt->cap_rows = ((rt->cap_items * MAX_SEQ + 127) / 128) * 128;
+    rt->cap_rows = ((rt->cap_items * MAX_SEQ + 255) / 256) * 256;
     g_rt = rt.get();  // forward() and friends read capacity through g_rt
     auto bail = [&](int rc) { g_rt = nullptr; return rc; };
     if (int rc = load_driver_entry()) return bail(rc);
@@ -910,18 +929,25 @@ int b200rt_debug_gemm(int epi, const uint16_t* a, const uint16_t* w, const float
     if (epi == 2) {
         if (!resid) return fail(B200RT_E_INVALID, "epi 2 needs resid");
         CUDA_TRY(cudaMalloc(&dr, Mp * N * 4));
+        CUDA_TRY(cudaMemset(dr, 0, Mp * N * 4));
         CUDA_TRY(cudaMemcpy(dr, resid, static_cast<size_t>(M) * N * 4, cudaMemcpyHostToDevice));
     }
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tout, tres;
     if (int rc = make_map_2d(&ta, da, Mp, K, 128)) return rc;
     if (int rc = make_map_2d(&tb, dw, N, K, 128)) return rc;
+    if (epi == 2) {
+        if (int rc = make_map_2d_f32(&tout, dout, Mp, N)) return rc;
+        if (int rc = make_map_2d_f32(&tres, dr, Mp, N)) return rc;
+    } else {
+        if (int rc = make_map_2d(&tout, dout, Mp, N, 128)) return rc;
+    }
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     if (iters < 1) iters = 1;
-    CUDA_TRY(launch_gemm(epi_full, ta, tb, db, dr, dout, M, N, K, d.sm_count, d.compute));  // warm-up + result
+    CUDA_TRY(launch_gemm(epi_full, ta, tb, tout, epi == 2 ? &tres : nullptr, db, M, N, K, d.sm_count, d.compute));  // warm-up + result
     CUDA_TRY(cudaEventRecord(e0, d.compute));
-    for (int i = 0; i < iters; ++i) CUDA_TRY(launch_gemm(epi_full, ta, tb, db, dr, dout, M, N, K, d.sm_count, d.compute));
+    for (int i = 0; i < iters; ++i) CUDA_TRY(launch_gemm(epi_full, ta, tb, tout, epi == 2 ? &tres : nullptr, db, M, N, K, d.sm_count, d.compute));
     CUDA_TRY(cudaEventRecord(e1, d.compute));
     CUDA_TRY(cudaStreamSynchronize(d.compute));
     float ms = 0;

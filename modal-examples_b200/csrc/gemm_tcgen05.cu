@@ -3,15 +3,24 @@
 // A cluster of two CTAs (one TPC) owns a 256 x 256 output tile.  CTA r of the pair TMA-loads its own
 // 128 rows of A and its own 128 rows (= output columns) of W per 64-wide k-block, so each SM pulls
 // 32 KB per k-block from L2 instead of the 48 KB a lone 128x256 CTA needs (the first, single-CTA version of
-// this kernel ran into the ~10 TB/s L2->smem fill limit at ~900 TFLOP/s; see profiles/README.md).
+// this kernel ran into the ~9.5 TB/s L2->SM fill limit at ~900 TFLOP/s; see profiles/README.md).
 // The leader CTA's single MMA thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16); each
 // CTA's TMEM receives its 128 rows x 256 fp32 columns, double buffered (2 x 256 columns), and each
-// CTA's 8 epilogue warps drain them (bias / erf-GELU / fp32 residual add) while the next tile's MMAs run.
+// CTA's 8 epilogue warps drain them while the next tile's MMAs run.
+//
+// Epilogue data movement is TMA on both sides: a row-per-thread LDG/STG touches 32 different 128-byte
+// lines per warp instruction (32 L1 wavefronts), which made the fp32 residual epilogue LSU-bound.  Instead
+// each column half of the tile (4 warps, thread = row) works on 128-row x 128-byte staging buffers in
+// shared memory (128B-swizzled, so a thread's 16-byte accesses are bank-conflict free per quarter warp):
+//   EPI_BIAS_RES_F32 : a DMA thread TMA-loads the fp32 residual chunk [128 x 32] into the buffer, the
+//                      compute threads add accumulator + bias in place, the DMA thread TMA-stores it to y.
+//   EPI_BIAS(_GELU)_F16 : compute threads write fp16 [128 x 64] chunks, the DMA thread TMA-stores them.
 //
 //   full[s]   (leader's)  : leader producer arrive.expect_tx(64 KB); both CTAs' TMA loads complete_tx on it
 //   empty[s]  (per CTA)   : tcgen05.commit multicast to both CTAs once the MMAs that read stage s retire
 //   tfull[a]  (per CTA)   : commit multicast after a tile's last MMA
 //   tempty[a] (leader's)  : 2 x 8 epilogue warps arrive (the peer's through mapa / shared::cluster)
+//   rfull[h][b] / cdone[h][b] (per CTA): staging buffer b of column half h is loaded/free  /  computed
 //
 // Replaces (inside TEI, un-vendored; restated from HF modeling_bert.py): the Linear layers of
 // BertSelfAttention :143-207 (fused QKV), BertSelfOutput.dense :287-298, BertIntermediate :330-342
@@ -24,13 +33,17 @@ namespace gemm {
 
 constexpr int BM = 128;        // rows per CTA (256 per pair)
 constexpr int BN = 256;        // columns per pair tile; each CTA stages 128 of them
-constexpr int BK = 64, STAGES = 6;
+constexpr int BK = 64, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;            // 16 KB
 constexpr int B_BYTES = (BN / 2) * BK * 2;      // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 32 KB per CTA
+constexpr int EBUF_BYTES = 128 * 128;           // one staging buffer: 128 rows x 128 bytes
+constexpr int OFF_EBUF = STAGES * STAGE_BYTES;  // [2 halves][2 buffers]
+constexpr int OFF_BIAS = OFF_EBUF + 4 * EBUF_BYTES;  // float [2 parities][256]
+constexpr int OFF_BAR = OFF_BIAS + 2 * 256 * 4;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 
 __device__ __forceinline__ float gelu_erf(float x) {
     // x * Phi(x), erf by Abramowitz-Stegun 7.1.26 (abs err <= 1.5e-7): 2 MUFU + ~12 FMA-pipe ops
@@ -50,16 +63,19 @@ __device__ __forceinline__ float gelu_erf(float x) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const float* __restrict__ bias, const float* __restrict__ resid, void* __restrict__ out, int M, int N,
-                 int K, int dbg_mode) {
+                 const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
+                 const float* __restrict__ bias, int M, int N, int K, int dbg_mode) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* full = bars;                     // [STAGES]
     uint64_t* empty = bars + STAGES;           // [STAGES]
     uint64_t* tfull = bars + 2 * STAGES;       // [2]
     uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* rfull = bars + 2 * STAGES + 4;   // [2 halves][2 buffers]
+    uint64_t* cdone = bars + 2 * STAGES + 8;   // [2 halves][2 buffers]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
+    float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS);
 
     const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
     const int lane = lane_id();
@@ -73,10 +89,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int kblocks = K / BK;
     const int nstages = (dbg_mode >> 4) ? (dbg_mode >> 4) : STAGES;  // diagnostics may use a shorter ring
     const int dmode = dbg_mode & 0xF;
+    // staging-buffer fills per tile per column half: fp32 [128x32] x 4, or fp16 [128x64] x 2
+    constexpr int NBUF_PER_TILE = (EPI == EPI_BIAS_RES_F32) ? 4 : 2;
 
     if (warp == 0 && elect_one()) {
         prefetch_tmap(&tma_a);
         prefetch_tmap(&tma_b);
+        prefetch_tmap(&tma_out);
+        if (EPI == EPI_BIAS_RES_F32) prefetch_tmap(&tma_res);
     }
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < STAGES; ++s) {
@@ -86,6 +106,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tfull[s], 1);
             mbar_init(&tempty[s], 2 * NUM_EPI_WARPS);
+        }
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(&rfull[s], 1);
+            mbar_init(&cdone[s], 128);
         }
         fence_barrier_init();
     }
@@ -151,84 +175,127 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 if (as == 0) aphase ^= 1;
             }
         }
-    } else if (warp >= 4) {
-        // -------------------------------------------------------------------- epilogue warps (both CTAs)
-        const int ew = warp & 3;           // TMEM lanes [32*ew, 32*ew+32)
-        const int half = (warp - 4) >> 2;  // which 128 columns of the tile
-        constexpr int CHUNKS = BN / 2 / 32;
-        int as = 0;
-        uint32_t aphase = 0;
-        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-            const int m_blk = tile / num_n, n_blk = tile % num_n;
-            const int row = m_blk * (2 * BM) + cta_rank * BM + ew * 32 + lane;
-            const bool row_ok = row < M;
-            const int col0 = n_blk * BN + half * (BN / 2);
-            const size_t row_off = static_cast<size_t>(row) * N + col0;
-            float4 rq[8];  // residual chunk, prefetched: it does not depend on the MMA
-            if constexpr (EPI == EPI_BIAS_RES_F32) {
-                if (row_ok) {
-                    const float4* r4 = reinterpret_cast<const float4*>(resid + row_off);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) rq[j] = r4[j];
+    } else if (warp == 3) {
+        if (lane < 2) {
+            // ---------------------------------------------------------------- epilogue DMA threads (one per column half)
+            const int h = lane;
+            uint8_t* ebuf = smem + OFF_EBUF + h * (2 * EBUF_BYTES);
+            int my_tiles = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) ++my_tiles;
+            const int total = my_tiles * NBUF_PER_TILE;
+            auto coords = [&](int g, int& c0, int& c1) {
+                const int tile = pair + (g / NBUF_PER_TILE) * num_pairs;
+                const int m_blk = tile / num_n, n_blk = tile % num_n;
+                const int sub = g % NBUF_PER_TILE;
+                c0 = n_blk * BN + h * (BN / 2) + sub * (EPI == EPI_BIAS_RES_F32 ? 32 : 64);
+                c1 = m_blk * (2 * BM) + cta_rank * BM;
+            };
+            auto fill = [&](int g) {  // make buffer g&1 ready for the compute threads
+                const int b = g & 1;
+                if constexpr (EPI == EPI_BIAS_RES_F32) {
+                    int c0, c1;
+                    coords(g, c0, c1);
+                    mbar_arrive_expect_tx(&rfull[h * 2 + b], EBUF_BYTES);
+                    tma_load_2d(ebuf + b * EBUF_BYTES, &tma_res, &rfull[h * 2 + b], c0, c1);
+                } else {
+                    mbar_arrive(&rfull[h * 2 + b]);  // nothing to load: just "buffer is free"
+                }
+            };
+            if (total > 0) fill(0);
+            if (total > 1) fill(1);
+            for (int g = 0; g < total; ++g) {
+                const int b = g & 1;
+                mbar_wait(&cdone[h * 2 + b], (g >> 1) & 1);
+                int c0, c1;
+                coords(g, c0, c1);
+                tma_store_2d(&tma_out, ebuf + b * EBUF_BYTES, c0, c1);
+                tma_store_commit();
+                if (g + 2 < total) {
+                    tma_store_wait_read<0>();  // the store has finished reading buffer b
+                    fill(g + 2);
                 }
             }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before the CTA may exit
+        }
+    } else if (warp >= 4) {
+        // -------------------------------------------------------------------- epilogue compute warps (both CTAs)
+        const int ew = warp & 3;         // TMEM lanes [32*ew, 32*ew+32)
+        const int h = (warp - 4) >> 2;   // which 128 columns of the tile
+        const int r = ew * 32 + lane;    // row within the CTA's 128 rows == index within the half
+        uint8_t* ebuf = smem + OFF_EBUF + h * (2 * EBUF_BYTES);
+        const uint32_t swz = static_cast<uint32_t>(r & 7);
+        int as = 0;
+        uint32_t aphase = 0;
+        uint32_t g = 0;  // staging-buffer use counter of this half
+        int tpar = 0;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs, tpar ^= 1) {
+            const int n_blk = tile % num_n;
+            // stage this tile's bias slice (128 floats per half) once; double buffered across tiles
+            float* sb = sbias + tpar * 256 + h * 128;
+            sb[r] = __ldg(bias + n_blk * BN + h * (BN / 2) + r);
+            named_bar_sync(1 + h, 128);
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < CHUNKS; ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + half * (BN / 2) + c * 32, r);
-                float4 rn[8];
-                if constexpr (EPI == EPI_BIAS_RES_F32) {
-                    if (row_ok && c + 1 < CHUNKS) {
-                        const float4* r4 = reinterpret_cast<const float4*>(resid + row_off + (c + 1) * 32);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) rn[j] = r4[j];
-                    }
-                }
-                const float4* b4 = reinterpret_cast<const float4*>(bias + col0 + c * 32);
-                float4 bq[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) bq[j] = __ldg(b4 + j);
-                tmem_ld_wait();
-                float v[32];
+            for (int c = 0; c < 4; ++c) {
+                uint32_t acc[32];
+                tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + h * (BN / 2) + c * 32, acc);
+                float bv[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bq[j].x;
-                    v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bq[j].y;
-                    v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bq[j].z;
-                    v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bq[j].w;
+                    const float4 b4 = *reinterpret_cast<const float4*>(sb + c * 32 + 4 * j);  // broadcast read
+                    bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
                 }
+                const uint32_t b = g & 1;
+                uint8_t* row_ptr = ebuf + b * EBUF_BYTES + r * 128;
                 if constexpr (EPI == EPI_BIAS_RES_F32) {
-                    if (row_ok) {
-                        float4* o4 = reinterpret_cast<float4*>(static_cast<float*>(out) + row_off + c * 32);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            o4[j] = make_float4(v[4 * j] + rq[j].x, v[4 * j + 1] + rq[j].y, v[4 * j + 2] + rq[j].z,
-                                                v[4 * j + 3] + rq[j].w);
-                        }
+                    mbar_wait(&rfull[h * 2 + b], (g >> 1) & 1);  // residual chunk has landed
+                    tmem_ld_wait();
+                    if (c == 3) {  // last TMEM read of this tile: release the accumulator to the MMA warp early
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(&tempty[as], 0);
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) rq[j] = rn[j];
+                    for (int q = 0; q < 8; ++q) {
+                        float4* p = reinterpret_cast<float4*>(row_ptr + ((static_cast<uint32_t>(q) ^ swz) << 4));
+                        const float4 rs = *p;
+                        *p = make_float4(__uint_as_float(acc[4 * q]) + bv[4 * q] + rs.x,
+                                         __uint_as_float(acc[4 * q + 1]) + bv[4 * q + 1] + rs.y,
+                                         __uint_as_float(acc[4 * q + 2]) + bv[4 * q + 2] + rs.z,
+                                         __uint_as_float(acc[4 * q + 3]) + bv[4 * q + 3] + rs.w);
+                    }
+                    fence_proxy_async_smem();
+                    mbar_arrive(&cdone[h * 2 + b]);
+                    ++g;
                 } else {
-                    if constexpr (EPI == EPI_BIAS_GELU_F16) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                    if ((c & 1) == 0) mbar_wait(&rfull[h * 2 + b], (g >> 1) & 1);  // buffer is free
+                    tmem_ld_wait();
+                    if (c == 3) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(&tempty[as], 0);
                     }
-                    if (row_ok) {
-                        uint4* o4 = reinterpret_cast<uint4*>(static_cast<__half*>(out) + row_off + c * 32);
+                    float v[32];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            o4[j] = make_uint4(pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
-                                               pack_half2(v[8 * j + 4], v[8 * j + 5]),
-                                               pack_half2(v[8 * j + 6], v[8 * j + 7]));
-                        }
+                    for (int j = 0; j < 32; ++j) {
+                        v[j] = __uint_as_float(acc[j]) + bv[j];
+                        if constexpr (EPI == EPI_BIAS_GELU_F16) v[j] = gelu_erf(v[j]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + q) ^ swz;
+                        *reinterpret_cast<uint4*>(row_ptr + (chunk << 4)) =
+                            make_uint4(pack_half2(v[8 * q], v[8 * q + 1]), pack_half2(v[8 * q + 2], v[8 * q + 3]),
+                                       pack_half2(v[8 * q + 4], v[8 * q + 5]), pack_half2(v[8 * q + 6], v[8 * q + 7]));
+                    }
+                    if (c & 1) {
+                        fence_proxy_async_smem();
+                        mbar_arrive(&cdone[h * 2 + b]);
+                        ++g;
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&tempty[as], 0);  // the leader's barrier gates the next MMA chain
             as ^= 1;
             if (as == 0) aphase ^= 1;
         }
@@ -247,12 +314,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 }  // namespace gemm
 
 template <int EPI>
-static cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid,
-                               void* out, int M, int N, int K, int sm_count, cudaStream_t stream, int dbg_mode) {
+static cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tres,
+                               const float* bias, int M, int N, int K, int sm_count, cudaStream_t stream, int dbg_mode) {
     const int tiles = ((M + 2 * gemm::BM - 1) / (2 * gemm::BM)) * (N / gemm::BN);
     int pairs = sm_count / 2;
     if (tiles < pairs) pairs = tiles;
-    gemm::gemm_pair_kernel<EPI><<<2 * pairs, gemm::NUM_THREADS, gemm::SMEM_BYTES, stream>>>(ta, tb, bias, resid, out, M, N, K, dbg_mode);
+    gemm::gemm_pair_kernel<EPI><<<2 * pairs, gemm::NUM_THREADS, gemm::SMEM_BYTES, stream>>>(ta, tb, tout, tres, bias, M, N, K, dbg_mode);
     return cudaGetLastError();
 }
 
@@ -265,17 +332,19 @@ cudaError_t gemm_init_device() {
     return cudaFuncSetAttribute(gemm::gemm_pair_kernel<EPI_BIAS_RES_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES);
 }
 
-// tb: 2D map over W {K, N} with box {64, 128} (each CTA stages half of the tile's columns).  Bits 8+ of `epi`
-// select a diagnostic mode (1 = no TMA loads, 2 = no MMA) used only by tools/gemm_diag.py.
-cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid,
-                             void* out, int M, int N, int K, int sm_count, cudaStream_t stream) {
+// Bits 8+ of `epi` select a diagnostic mode (low nibble: 1 = no TMA loads, 2 = no MMA; high nibble: ring
+// length) used only by tools/gemm_diag.py.
+cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap* tres,
+                        const float* bias, int M, int N, int K, int sm_count, cudaStream_t stream) {
     const int dbg_mode = epi >> 8;
     epi &= 0xFF;
     if (N % gemm::BN != 0 || K % gemm::BK != 0 || M <= 0) return cudaErrorInvalidValue;
+    if (epi == EPI_BIAS_RES_F32 && !tres) return cudaErrorInvalidValue;
+    const CUtensorMap& tr = tres ? *tres : tout;
     switch (epi) {
-        case EPI_BIAS_F16: return launch_pair<EPI_BIAS_F16>(ta, tb, bias, resid, out, M, N, K, sm_count, stream, dbg_mode);
-        case EPI_BIAS_GELU_F16: return launch_pair<EPI_BIAS_GELU_F16>(ta, tb, bias, resid, out, M, N, K, sm_count, stream, dbg_mode);
-        case EPI_BIAS_RES_F32: return launch_pair<EPI_BIAS_RES_F32>(ta, tb, bias, resid, out, M, N, K, sm_count, stream, dbg_mode);
+        case EPI_BIAS_F16: return launch_pair<EPI_BIAS_F16>(ta, tb, tout, tr, bias, M, N, K, sm_count, stream, dbg_mode);
+        case EPI_BIAS_GELU_F16: return launch_pair<EPI_BIAS_GELU_F16>(ta, tb, tout, tr, bias, M, N, K, sm_count, stream, dbg_mode);
+        case EPI_BIAS_RES_F32: return launch_pair<EPI_BIAS_RES_F32>(ta, tb, tout, tr, bias, M, N, K, sm_count, stream, dbg_mode);
     }
     return cudaErrorInvalidValue;
 }

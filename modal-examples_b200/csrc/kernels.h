@@ -21,10 +21,13 @@ constexpr int QKV_DIM = 3 * HIDDEN;
 // One-time per-device setup (dynamic shared memory opt-in for every kernel). Call with the device current.
 cudaError_t kernels_init_device();
 
-// C[M,N] = epi(A[M,K] . W[N,K]^T + bias) on CTA pairs.  ta: 2D map over A {K, rows>=M}, box {64,128}, 128B swizzle;
-// tb: 2D map over W {K, N}, box {64,128}, 128B swizzle.  N % 256 == 0, K % 64 == 0.
-cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const float* bias, const float* resid,
-                        void* out, int M, int N, int K, int sm_count, cudaStream_t stream);
+// C[M,N] = epi(A[M,K] . W[N,K]^T + bias) on CTA pairs.  All operands move by TMA (128B swizzle):
+//   ta  : fp16 A   {K, rows>=M}  box {64,128}        tb  : fp16 W {K, N} box {64,128}
+//   tout: fp16 out {N, rows} box {64,128} (EPI 0/1)  or  fp32 out {N, rows} box {32,128} (EPI 2)
+//   tres: fp32 residual {N, rows} box {32,128} (EPI 2 only, else NULL).  rows must cover ceil(M/256)*256
+//         or the maps' own bounds clip the tail.  N % 256 == 0, K % 64 == 0.
+cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap* tres,
+                        const float* bias, int M, int N, int K, int sm_count, cudaStream_t stream);
 
 // Multi-head self-attention over a padded batch: qkv fp16 [B, S, 2304] (Q | K | V, head-major within each),
 // lens[B] valid keys per item, ctx fp16 [B*S, 768].  tq: 3D map over qkv {2304, S, B}, box {64,128,1}, 128B swizzle.
