@@ -48,7 +48,13 @@ constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restrict__ lens, __half* __restrict__ ctx,
-                 int S) {
+                 int S, unsigned long long* __restrict__ dbg) {
+    // dbg (diagnostics only, normally NULL): CTA 0 records clock64() stamps, 16 slots per query tile for each of
+    // three observers (softmax warpgroup 0 / 1 lane 0, MMA thread)
+#define ATT_STAMP(obs, qt, slot)                                                            \
+    do {                                                                                    \
+        if (dbg != nullptr && blockIdx.x == 0) dbg[((obs) * 8 + (qt)) * 16 + (slot)] = clock64(); \
+    } while (0)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -130,6 +136,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
                 mbar_wait(&q_full[slot], (qt >> 1) & 1);
                 if (qt > 0) mbar_wait(tmem_free, (qt - 1) & 1);
                 tc_fence_after();
+                ATT_STAMP(2, qt, 0);
                 const uint32_t q_addr = smem_u32(smem + OFF_Q + slot * TILE_BYTES);
                 for (int j = 0; j < nkb; ++j) {
 #pragma unroll
@@ -140,11 +147,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
                     umma_commit(&s_full[j]);
                 }
                 umma_commit(&q_empty[slot]);
+                ATT_STAMP(2, qt, 1);
                 if (qt == 0) mbar_wait(v_full, 0);
                 for (int sb = 0; sb < nsb; ++sb) {
                     const uint32_t pb = pcount % PRING;
                     mbar_wait(&p_full[pb], (pcount / PRING) & 1);
                     tc_fence_after();
+                    ATT_STAMP(2, qt, 2 + sb);
 #pragma unroll
                     for (int kk = 0; kk < SB / 16; ++kk) {
                         const uint32_t a = p_addr + pb * TILE_BYTES + kk * 32;
@@ -155,6 +164,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
                     ++pcount;
                 }
                 umma_commit(o_full);
+                ATT_STAMP(2, qt, 10);
             }
         }
     } else if (warp >= 4) {
@@ -164,13 +174,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
         const int r = (e & 3) * 32 + lane;    // query row within the tile == TMEM lane
         const uint32_t lane_base = static_cast<uint32_t>((e & 3) * 32) << 16;
         uint8_t* p_base = smem + OFF_P;
+        const bool obs = (e & 3) == 0 && lane == 0;
         for (int qt = 0; qt < nq; ++qt) {
+            if (obs) ATT_STAMP(g, qt, 0);
 #pragma unroll 1
             for (int j = 0; j < nkb; ++j) {
                 const int sb = 2 * j + g;
                 if (sb >= nsb) break;
                 mbar_wait(&s_full[j], qt & 1);
                 tc_fence_after();
+                if (obs) ATT_STAMP(g, qt, 1 + 2 * j);
                 const int valid = len - sb * SB;  // keys [0, valid) of this sub-block are real (>= 1)
                 uint32_t v[64];
                 tmem_ld_32x32b_x32(tmem_base + lane_base + sb * SB, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
@@ -211,9 +224,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
                 tc_fence_before();         // our TMEM reads of S_sb precede the MMA that overwrites it with O_sb
                 fence_proxy_async_smem();  // P_sb visible to the tensor core's async-proxy reads
                 mbar_arrive(&p_full[pb]);
+                if (obs) ATT_STAMP(g, qt, 2 + 2 * j);
             }
+            if (obs) ATT_STAMP(g, qt, 9);
             // every (m, l) of this tile is in smem once all softmax threads are here
             named_bar_sync(1, NUM_SOFTMAX_THREADS);
+            if (obs) ATT_STAMP(g, qt, 10);
             float m_all = -INFINITY;
             for (int sb = 0; sb < nsb; ++sb) m_all = fmaxf(m_all, ml[sb * QT + r].x);
             float w[MAX_SB];
@@ -231,6 +247,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
             const float inv_l = 1.0f / L;
             mbar_wait(o_full, qt & 1);
             tc_fence_after();
+            if (obs) ATT_STAMP(g, qt, 11);
             float acc[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[i] = 0.f;
@@ -246,6 +263,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
             }
             tc_fence_before();
             mbar_arrive(tmem_free);  // also orders our reads of `ml` before the next tile's writes
+            if (obs) ATT_STAMP(g, qt, 12);
             const int q_row = qt * QT + r;
             if (q_row < S) {
                 uint4* dst = reinterpret_cast<uint4*>(ctx + (static_cast<size_t>(b) * S + q_row) * HIDDEN + h * D + g * 32);
@@ -275,9 +293,9 @@ cudaError_t attention_init_device() {
 }
 
 cudaError_t launch_attention(const CUtensorMap& tq, const int32_t* lens, __half* ctx, int B, int S,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, unsigned long long* dbg) {
     if (S < 1 || S > attn::MAX_KB * attn::KB || B < 1) return cudaErrorInvalidValue;
-    attn::attention_kernel<<<B * HEADS, attn::NUM_THREADS, attn::SMEM_BYTES, stream>>>(tq, lens, ctx, S);
+    attn::attention_kernel<<<B * HEADS, attn::NUM_THREADS, attn::SMEM_BYTES, stream>>>(tq, lens, ctx, S, dbg);
     return cudaGetLastError();
 }
 

@@ -990,6 +990,28 @@ int b200rt_debug_attention(const uint16_t* qkv, const int32_t* lens, uint16_t* c
     cudaEventElapsedTime(&ms, e0, e1);
     if (ms_out) *ms_out = ms / iters;
     CUDA_TRY(cudaMemcpy(ctx, dc, M * HIDDEN * 2, cudaMemcpyDeviceToHost));
+    if (getenv("B200RT_ATTN_STAMPS")) {  // diagnostics: per-phase clock stamps of CTA 0
+        unsigned long long* dstamp = nullptr;
+        std::vector<unsigned long long> hs(3 * 8 * 16, 0);
+        CUDA_TRY(cudaMalloc(&dstamp, hs.size() * 8));
+        CUDA_TRY(cudaMemset(dstamp, 0, hs.size() * 8));
+        CUDA_TRY(launch_attention(tq, dl_, dc, B, S, d.compute, dstamp));
+        CUDA_TRY(cudaStreamSynchronize(d.compute));
+        CUDA_TRY(cudaMemcpy(hs.data(), dstamp, hs.size() * 8, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = ~0ull;
+        for (auto v : hs) if (v && v < t0) t0 = v;
+        const char* names[3] = {"softmax_g0", "softmax_g1", "mma"};
+        for (int o = 0; o < 3; ++o)
+            for (int qt = 0; qt < 4; ++qt) {
+                printf("stamps %s qt%d:", names[o], qt);
+                for (int sl = 0; sl < 13; ++sl) {
+                    unsigned long long v = hs[(o * 8 + qt) * 16 + sl];
+                    if (v) printf(" [%d]=%llu", sl, v - t0); else printf(" [%d]=-", sl);
+                }
+                printf("\n");
+            }
+        cudaFree(dstamp);
+    }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(dq); cudaFree(dc); cudaFree(dl_);
     return 0;

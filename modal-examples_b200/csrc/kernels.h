@@ -32,7 +32,7 @@ cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
 // Multi-head self-attention over a padded batch: qkv fp16 [B, S, 2304] (Q | K | V, head-major within each),
 // lens[B] valid keys per item, ctx fp16 [B*S, 768].  tq: 3D map over qkv {2304, S, B}, box {64,128,1}, 128B swizzle.
 cudaError_t launch_attention(const CUtensorMap& tq, const int32_t* lens, __half* ctx, int B, int S,
-                             cudaStream_t stream);
+                             cudaStream_t stream, unsigned long long* dbg = nullptr);
 
 // word + position + token_type(0) embedding gather, LayerNorm -> x32 (fp32 residual stream) and x16 (GEMM input)
 cudaError_t launch_embed_ln(const int32_t* ids, const float* word, const float* pos, const float* type0,
