@@ -192,7 +192,7 @@ struct Wave {
 
 struct Runtime {
     std::vector<std::unique_ptr<Dev>> devs;
-    int cap_items = 64;  // per replica per wave, at 512 tokens
+    int cap_items = 128;  // per replica per wave, at 512 tokens (128 fills the 74 CTA pairs ~10% better than 64)
     int cap_rows = 0;    // cap_items*512 rounded up to 128
     std::vector<std::unique_ptr<Model>> models;
     // root staging per slot
@@ -990,9 +990,9 @@ int b200rt_debug_attention(const uint16_t* qkv, const int32_t* lens, uint16_t* c
     cudaEventElapsedTime(&ms, e0, e1);
     if (ms_out) *ms_out = ms / iters;
     CUDA_TRY(cudaMemcpy(ctx, dc, M * HIDDEN * 2, cudaMemcpyDeviceToHost));
-    if (getenv("B200RT_ATTN_STAMPS")) {  // diagnostics: per-phase clock stamps of CTA 0
+    if (const char* path = getenv("B200RT_ATTN_STAMPS")) {  // diagnostics: per-phase clock stamps of CTA 0 -> text file
         unsigned long long* dstamp = nullptr;
-        std::vector<unsigned long long> hs(3 * 8 * 16, 0);
+        std::vector<unsigned long long> hs(4 * 32 * 8, 0);
         CUDA_TRY(cudaMalloc(&dstamp, hs.size() * 8));
         CUDA_TRY(cudaMemset(dstamp, 0, hs.size() * 8));
         CUDA_TRY(launch_attention(tq, dl_, dc, B, S, d.compute, dstamp));
@@ -1000,16 +1000,22 @@ int b200rt_debug_attention(const uint16_t* qkv, const int32_t* lens, uint16_t* c
         CUDA_TRY(cudaMemcpy(hs.data(), dstamp, hs.size() * 8, cudaMemcpyDeviceToHost));
         unsigned long long t0 = ~0ull;
         for (auto v : hs) if (v && v < t0) t0 = v;
-        const char* names[3] = {"softmax_g0", "softmax_g1", "mma"};
-        for (int o = 0; o < 3; ++o)
-            for (int qt = 0; qt < 4; ++qt) {
-                printf("stamps %s qt%d:", names[o], qt);
-                for (int sl = 0; sl < 13; ++sl) {
-                    unsigned long long v = hs[(o * 8 + qt) * 16 + sl];
-                    if (v) printf(" [%d]=%llu", sl, v - t0); else printf(" [%d]=-", sl);
+        if (FILE* f = fopen(path, "w")) {
+            const char* names[4] = {"softmax_m0", "softmax_m1", "mma_m0", "mma_m1"};
+            for (int o = 0; o < 4; ++o)
+                for (int c = 0; c < 32; ++c) {
+                    bool any = false;
+                    for (int sl = 0; sl < 8; ++sl) any |= hs[(o * 32 + c) * 8 + sl] != 0;
+                    if (!any) continue;
+                    fprintf(f, "%s c%02d:", names[o], c);
+                    for (int sl = 0; sl < 8; ++sl) {
+                        unsigned long long v = hs[(o * 32 + c) * 8 + sl];
+                        if (v) fprintf(f, " %llu", v - t0); else fprintf(f, " -");
+                    }
+                    fprintf(f, "\n");
                 }
-                printf("\n");
-            }
+            fclose(f);
+        }
         cudaFree(dstamp);
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -286,7 +286,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
-    asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // pure: let the scheduler interleave it freely
     return y;
 }
 

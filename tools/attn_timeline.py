@@ -1,7 +1,11 @@
+#!/usr/bin/env python
+"""Diagnostics: dump CTA 0's per-sub-block clock stamps of the attention kernel (B200RT_ATTN_STAMPS)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "modal-examples_b200"))
-os.environ["B200RT_ATTN_STAMPS"] = "1"
+out = os.path.join(ROOT, "gpurun_out", "attn_timeline.txt")
+os.makedirs(os.path.dirname(out), exist_ok=True)
+os.environ["B200RT_ATTN_STAMPS"] = out
 import numpy as np, b200rt
 b200rt.init(1)
 rng = np.random.default_rng(0)
@@ -9,3 +13,4 @@ B, S = 64, 512
 qkv = rng.standard_normal((B * S, 2304)).astype(np.float16)
 ctx, ms = b200rt.debug_attention(qkv, np.full(B, S, np.int32), B, S, iters=5)
 print("ms", ms)
+print(open(out).read())

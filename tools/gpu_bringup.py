@@ -245,7 +245,9 @@ def stage_perf(res):
     flat = R.make_weights(g, 0, "hf")
     model = b200rt.EmbedModel(R.geometry_dict(g), R.pack_blob(flat, g))
     res["profile"] = {}
-    for B in (32, 64):
+    for B in (32, 64, 128):
+        if B > b200rt.wave_capacity_items():
+            continue
         prof = model.profile_forward(B, 512, iters=3)
         total = sum(prof.values())
         res["profile"][str(B)] = dict(per_kernel_ms=prof, total_ms=total, items_per_s=B / total * 1e3,
