@@ -268,6 +268,18 @@ def main_ours(args):
     dev_out = d_out.cpu().numpy()
     assert float(np.abs(dev_out - e2e_out).max()) < 1e-5, "device-resident and host-buffer paths disagree"
 
+    # ---------------- p50 per-item latency: one 512-token item through the same C ABI, host buffers
+    one_ids = pin_ids.array[:1]
+    one_out = pin_out.array[:1]
+    lat = []
+    for i in range(120):
+        t1 = time.perf_counter()
+        model.wait(model.submit(one_ids, None, out=one_out))
+        if i >= 20:
+            lat.append((time.perf_counter() - t1) * 1e3)
+    lat.sort()
+    p50_ms, p99_ms = lat[len(lat) // 2], lat[int(len(lat) * 0.99) - 1]
+
     # ---------------- max over ranks
     if use_dist:
         t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
@@ -321,6 +333,7 @@ def main_ours(args):
                     "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // args.steps, "ms_per_step": e2e_s / args.steps * 1e3,
                     "api": "b200rt_submit/b200rt_wait (C ABI, pinned host buffers)"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "latency": {"p50_ms": p50_ms, "p99_ms": p99_ms, "what": "one 512-token item, b200rt_submit+b200rt_wait, pinned host buffers, 100 trials after 20 warm-ups (rank 0)"},
         }
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline

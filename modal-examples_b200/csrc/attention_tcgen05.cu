@@ -176,7 +176,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
         const int m = (warp - 4) >> 2;
         const int r = (warp & 3) * 32 + lane;  // query row within the tile == TMEM lane
         const uint32_t tm = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + m * 256;
-        uint8_t* p_base = smem + OFF_P + m * 2 * TILE_BYTES;
+        const uint32_t p_base = smem_u32(smem + OFF_P + m * 2 * TILE_BYTES);
         const uint32_t swz = static_cast<uint32_t>(r & 7);
         uint32_t c = 0;  // sub-block counter of this machine (continues across its tiles)
         const bool obs = (warp & 3) == 0 && lane == 0;
@@ -235,7 +235,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
                 mbar_wait(&p_empty[m * 2 + ps], ((c >> 1) & 1) ^ 1);
                 if (obs) ATT_STAMP(m, c, 3);
                 float ls0 = 0.f, ls1 = 0.f;
-                uint8_t* row_ptr = p_base + ps * TILE_BYTES + r * 128;
+                const uint32_t row_ptr = p_base + ps * TILE_BYTES + r * 128;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     uint32_t pk[4];
@@ -248,8 +248,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
                         pk[e] = pack_half2(p0, p1);
                     }
                     // keys 8q .. 8q+7 of row r -> 16-byte chunk q ^ (r & 7) of the row's 128 bytes
-                    *reinterpret_cast<uint4*>(row_ptr + ((static_cast<uint32_t>(q) ^ swz) << 4)) =
-                        make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    sts128(row_ptr + ((static_cast<uint32_t>(q) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
                 }
                 tc_fence_before();         // our TMEM reads of S_c precede the MMA that overwrites it with O_c
                 fence_proxy_async_smem();  // P_c visible to the tensor core's async-proxy reads

@@ -222,7 +222,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int ew = warp & 3;         // TMEM lanes [32*ew, 32*ew+32)
         const int h = (warp - 4) >> 2;   // which 128 columns of the tile
         const int r = ew * 32 + lane;    // row within the CTA's 128 rows == index within the half
-        uint8_t* ebuf = smem + OFF_EBUF + h * (2 * EBUF_BYTES);
+        const uint32_t ebuf = smem_u32(smem + OFF_EBUF + h * (2 * EBUF_BYTES));
         const uint32_t swz = static_cast<uint32_t>(r & 7);
         int as = 0;
         uint32_t aphase = 0;
@@ -231,8 +231,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int tile = pair; tile < num_tiles; tile += num_pairs, tpar ^= 1) {
             const int n_blk = tile % num_n;
             // stage this tile's bias slice (128 floats per half) once; double buffered across tiles
-            float* sb = sbias + tpar * 256 + h * 128;
-            sb[r] = __ldg(bias + n_blk * BN + h * (BN / 2) + r);
+            const uint32_t sb = smem_u32(sbias + tpar * 256 + h * 128);
+            sts32f(sb + r * 4, __ldg(bias + n_blk * BN + h * (BN / 2) + r));
             named_bar_sync(1 + h, 128);
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
@@ -243,11 +243,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 float bv[32];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(sb + c * 32 + 4 * j);  // broadcast read
+                    const float4 b4 = lds128f(sb + (c * 32 + 4 * j) * 4);  // broadcast read
                     bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
                 }
                 const uint32_t b = g & 1;
-                uint8_t* row_ptr = ebuf + b * EBUF_BYTES + r * 128;
+                const uint32_t row_ptr = ebuf + b * EBUF_BYTES + r * 128;
                 if constexpr (EPI == EPI_BIAS_RES_F32) {
                     mbar_wait(&rfull[h * 2 + b], (g >> 1) & 1);  // residual chunk has landed
                     tmem_ld_wait();
@@ -258,12 +258,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     }
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        float4* p = reinterpret_cast<float4*>(row_ptr + ((static_cast<uint32_t>(q) ^ swz) << 4));
-                        const float4 rs = *p;
-                        *p = make_float4(__uint_as_float(acc[4 * q]) + bv[4 * q] + rs.x,
-                                         __uint_as_float(acc[4 * q + 1]) + bv[4 * q + 1] + rs.y,
-                                         __uint_as_float(acc[4 * q + 2]) + bv[4 * q + 2] + rs.z,
-                                         __uint_as_float(acc[4 * q + 3]) + bv[4 * q + 3] + rs.w);
+                        const uint32_t p = row_ptr + ((static_cast<uint32_t>(q) ^ swz) << 4);
+                        const float4 rs = lds128f(p);
+                        sts128f(p, __uint_as_float(acc[4 * q]) + bv[4 * q] + rs.x, __uint_as_float(acc[4 * q + 1]) + bv[4 * q + 1] + rs.y,
+                                __uint_as_float(acc[4 * q + 2]) + bv[4 * q + 2] + rs.z, __uint_as_float(acc[4 * q + 3]) + bv[4 * q + 3] + rs.w);
                     }
                     fence_proxy_async_smem();
                     mbar_arrive(&cdone[h * 2 + b]);
@@ -285,9 +283,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + q) ^ swz;
-                        *reinterpret_cast<uint4*>(row_ptr + (chunk << 4)) =
-                            make_uint4(pack_half2(v[8 * q], v[8 * q + 1]), pack_half2(v[8 * q + 2], v[8 * q + 3]),
-                                       pack_half2(v[8 * q + 4], v[8 * q + 5]), pack_half2(v[8 * q + 6], v[8 * q + 7]));
+                        sts128(row_ptr + (chunk << 4), pack_half2(v[8 * q], v[8 * q + 1]), pack_half2(v[8 * q + 2], v[8 * q + 3]),
+                               pack_half2(v[8 * q + 4], v[8 * q + 5]), pack_half2(v[8 * q + 6], v[8 * q + 7]));
                     }
                     if (c & 1) {
                         fence_proxy_async_smem();

@@ -273,6 +273,25 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int a_mn = 0
            (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ------------------------------------------------------------------------------------ shared-memory accessors
+// Explicit .shared instructions on 32-bit shared addresses: pointer arithmetic on a generic `uint8_t*` makes the
+// compiler emit generic LD.E/ST.E (64-bit address math + address-space resolution) instead of LDS/STS.
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts32f(uint32_t addr, float a) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
+}
+
 // ------------------------------------------------------------------------------------ misc
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
