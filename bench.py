@@ -46,7 +46,7 @@ KERNEL_FLOPS = {
     "gemm_ffn2": 2 * 512 * 3072 * 768, "attention": 4 * 512 * 512 * 768,
 }
 # algorithmic HBM bytes per token of the row-wise kernels
-KERNEL_BYTES = {"embed_ln": 3072 + 3072 + 1536, "ln1": 3072 + 3072 + 1536, "ln2": 3072 + 3072 + 1536}
+KERNEL_BYTES = {"embed_ln": 3072 + 3072 + 1536 + 8, "ln1": 3072 + 1536 + 8, "ln2": 3072 + 1536 + 8}
 
 
 def load_peaks():

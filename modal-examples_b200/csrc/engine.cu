@@ -152,11 +152,13 @@ struct Dev {
     int sm_count = 148;
     cudaStream_t compute = nullptr;
     // workspace (capacity cap_rows rows)
-    float *x32 = nullptr, *y32 = nullptr;
+    float* y32 = nullptr;        // fp32 residual stream, PRE-LayerNorm
+    float2* stats = nullptr;     // (mean, rstd) per row of the LayerNorm last applied to y32
+    float* x32_dbg = nullptr;    // tests only (b200rt_debug_hidden): normalised fp32 rows, allocated on first use
     __half *x16 = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr;
     CUtensorMap m_x16, m_ctx, m_ffn;      // fp16 [rows,*] box {64,128}: GEMM A operands (m_ffn is also FFN1's output map)
     CUtensorMap m_qkv2d;                  // fp16 [rows,2304] box {64,128}: QKV GEMM output
-    CUtensorMap m_x32, m_y32;             // fp32 [rows,768] box {32,128}: residual in / pre-LN out of the fp32 epilogues
+    CUtensorMap m_y32;                    // fp32 [rows,768] box {32,128}: the fp32 epilogues update y32 in place
     std::unordered_map<int, CUtensorMap> m_qkv_by_S;
     // wave input slots (written by the root's scatter kernel, possibly over NVLink)
     int32_t* ids_in[NSLOT] = {nullptr, nullptr, nullptr};
@@ -242,7 +244,7 @@ int get_qkv_map(Dev& d, int S, const CUtensorMap** out) {
 }
 
 // Enqueue the forward of one padded batch [B, S] on `stream`.  out: fp32 [B, 768], may be peer memory.
-// n_layers < cfg.layers (debug): stop early and leave the post-LN hidden state in d.x32.
+// n_layers >= 0 (debug): stop early and materialise the post-LN hidden state in d.x32_dbg.
 int forward(Dev& d, const Model& m, int dev_index, const int32_t* ids, const int32_t* lens, int B, int S, float* out,
             cudaStream_t stream, int n_layers = -1, Prof* prof = nullptr, uint64_t* launches = nullptr) {
     const DevWeights& w = m.per_dev[dev_index];
@@ -264,7 +266,9 @@ int forward(Dev& d, const Model& m, int dev_index, const int32_t* ids, const int
         }
     };
     mark("begin");
-    CUDA_TRY(launch_embed_ln(ids, w.word, w.pos, w.type, w.emb_g, w.emb_b, d.x32, d.x16, M, S, c.vocab, c.eps, stream));
+    float* const dbg = full ? nullptr : d.x32_dbg;
+    CUDA_TRY(launch_embed_ln(ids, w.word, w.pos, w.type, w.emb_g, w.emb_b, d.y32, d.x16, d.stats, L == 0 ? dbg : nullptr, M, S, c.vocab, c.eps, stream));
+    LnRef prev{d.stats, w.emb_g, w.emb_b};  // the LayerNorm whose output is the current residual
     ++nl; mark("embed_ln");
     for (int l = 0; l < L; ++l) {
         const LayerW& lw = w.layers[l];
@@ -272,16 +276,18 @@ int forward(Dev& d, const Model& m, int dev_index, const int32_t* ids, const int
         ++nl; mark("gemm_qkv");
         CUDA_TRY(launch_attention(*mq, lens, d.ctx, B, S, stream));
         ++nl; mark("attention");
-        CUDA_TRY(launch_gemm(EPI_BIAS_RES_F32, d.m_ctx, lw.m_ao, d.m_y32, &d.m_x32, lw.ao_b, M, HIDDEN, HIDDEN, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_F32, d.m_ctx, lw.m_ao, d.m_y32, &prev, lw.ao_b, M, HIDDEN, HIDDEN, d.sm_count, stream));
         ++nl; mark("gemm_attn_out");
-        CUDA_TRY(launch_ln(d.y32, lw.ln1_g, lw.ln1_b, d.x32, d.x16, M, c.eps, stream));
+        CUDA_TRY(launch_ln(d.y32, lw.ln1_g, lw.ln1_b, d.x16, d.stats, nullptr, M, c.eps, stream));
+        prev = LnRef{d.stats, lw.ln1_g, lw.ln1_b};
         ++nl; mark("ln1");
         CUDA_TRY(launch_gemm(EPI_BIAS_GELU_F16, d.m_x16, lw.m_ff1, d.m_ffn, nullptr, lw.ff1_b, M, c.inter, HIDDEN, d.sm_count, stream));
         ++nl; mark("gemm_ffn1_gelu");
-        CUDA_TRY(launch_gemm(EPI_BIAS_RES_F32, d.m_ffn, lw.m_ff2, d.m_y32, &d.m_x32, lw.ff2_b, M, HIDDEN, c.inter, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_F32, d.m_ffn, lw.m_ff2, d.m_y32, &prev, lw.ff2_b, M, HIDDEN, c.inter, d.sm_count, stream));
         ++nl; mark("gemm_ffn2");
         if (!(full && l == L - 1)) {
-            CUDA_TRY(launch_ln(d.y32, lw.ln2_g, lw.ln2_b, d.x32, d.x16, M, c.eps, stream));
+            CUDA_TRY(launch_ln(d.y32, lw.ln2_g, lw.ln2_b, d.x16, d.stats, l == L - 1 ? dbg : nullptr, M, c.eps, stream));
+            prev = LnRef{d.stats, lw.ln2_g, lw.ln2_b};
             ++nl; mark("ln2");
         }
     }
@@ -488,14 +494,14 @@ int alloc_dev(Runtime& rt, Dev& d) {
     CUDA_TRY(kernels_init_device());
     CUDA_TRY(cudaStreamCreateWithFlags(&d.compute, cudaStreamNonBlocking));
     const size_t R = rt.cap_rows;
-    CUDA_TRY(cudaMalloc(&d.x32, R * HIDDEN * 4));
+    CUDA_TRY(cudaMalloc(&d.stats, R * sizeof(float2)));
+    CUDA_TRY(cudaMemset(d.stats, 0, R * sizeof(float2)));
     CUDA_TRY(cudaMalloc(&d.y32, R * HIDDEN * 4));
     CUDA_TRY(cudaMalloc(&d.x16, R * HIDDEN * 2));
     CUDA_TRY(cudaMalloc(&d.qkv, R * QKV_DIM * 2));
     CUDA_TRY(cudaMalloc(&d.ctx, R * HIDDEN * 2));
     CUDA_TRY(cudaMalloc(&d.ffn, R * 3072 * 2));
     // padded / stale rows must stay finite (0 * NaN would leak through masked attention probabilities)
-    CUDA_TRY(cudaMemset(d.x32, 0, R * HIDDEN * 4));
     CUDA_TRY(cudaMemset(d.y32, 0, R * HIDDEN * 4));
     CUDA_TRY(cudaMemset(d.x16, 0, R * HIDDEN * 2));
     CUDA_TRY(cudaMemset(d.qkv, 0, R * QKV_DIM * 2));
@@ -505,7 +511,6 @@ int alloc_dev(Runtime& rt, Dev& d) {
     if (int rc = make_map_2d(&d.m_ctx, d.ctx, R, HIDDEN, 128)) return rc;
     if (int rc = make_map_2d(&d.m_ffn, d.ffn, R, 3072, 128)) return rc;
     if (int rc = make_map_2d(&d.m_qkv2d, d.qkv, R, QKV_DIM, 128)) return rc;
-    if (int rc = make_map_2d_f32(&d.m_x32, d.x32, R, HIDDEN)) return rc;
     if (int rc = make_map_2d_f32(&d.m_y32, d.y32, R, HIDDEN)) return rc;
     for (int s = 0; s < NSLOT; ++s) {
         CUDA_TRY(cudaMalloc(&d.ids_in[s], R * 4));
@@ -884,7 +889,7 @@ void b200rt_shutdown(void) {
         }
     for (auto& d : rt->devs) {
         cudaSetDevice(d->id);
-        cudaFree(d->x32); cudaFree(d->y32); cudaFree(d->x16); cudaFree(d->qkv); cudaFree(d->ctx); cudaFree(d->ffn);
+        cudaFree(d->x32_dbg); cudaFree(d->stats); cudaFree(d->y32); cudaFree(d->x16); cudaFree(d->qkv); cudaFree(d->ctx); cudaFree(d->ffn);
         for (int s = 0; s < NSLOT; ++s) { cudaFree(d->ids_in[s]); cudaFree(d->lens_in[s]); cudaEventDestroy(d->ev_done[s]); }
         cudaStreamDestroy(d->compute);
     }
@@ -932,23 +937,27 @@ int b200rt_debug_gemm(int epi, const uint16_t* a, const uint16_t* w, const float
         CUDA_TRY(cudaMemset(dr, 0, Mp * N * 4));
         CUDA_TRY(cudaMemcpy(dr, resid, static_cast<size_t>(M) * N * 4, cudaMemcpyHostToDevice));
     }
-    CUtensorMap ta, tb, tout, tres;
+    CUtensorMap ta, tb, tout;
     if (int rc = make_map_2d(&ta, da, Mp, K, 128)) return rc;
     if (int rc = make_map_2d(&tb, dw, N, K, 128)) return rc;
     if (epi == 2) {
         if (int rc = make_map_2d_f32(&tout, dout, Mp, N)) return rc;
-        if (int rc = make_map_2d_f32(&tres, dr, Mp, N)) return rc;
     } else {
         if (int rc = make_map_2d(&tout, dout, Mp, N, 128)) return rc;
     }
+    // epi 2 updates `out` in place (out = acc + bias + out): reload the residual before every launch
+    auto reload = [&]() -> cudaError_t {
+        return epi == 2 ? cudaMemcpyAsync(dout, dr, Mp * N * 4, cudaMemcpyDeviceToDevice, d.compute) : cudaSuccess;
+    };
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     if (iters < 1) iters = 1;
-    CUDA_TRY(launch_gemm(epi_full, ta, tb, tout, epi == 2 ? &tres : nullptr, db, M, N, K, d.sm_count, d.compute));  // warm-up + result
     CUDA_TRY(cudaEventRecord(e0, d.compute));
-    for (int i = 0; i < iters; ++i) CUDA_TRY(launch_gemm(epi_full, ta, tb, tout, epi == 2 ? &tres : nullptr, db, M, N, K, d.sm_count, d.compute));
+    for (int i = 0; i < iters; ++i) CUDA_TRY(launch_gemm(epi_full, ta, tb, tout, nullptr, db, M, N, K, d.sm_count, d.compute));  // timing (values drift in place)
     CUDA_TRY(cudaEventRecord(e1, d.compute));
+    CUDA_TRY(reload());
+    CUDA_TRY(launch_gemm(epi_full, ta, tb, tout, nullptr, db, M, N, K, d.sm_count, d.compute));  // the result that is returned
     CUDA_TRY(cudaStreamSynchronize(d.compute));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
@@ -1043,10 +1052,11 @@ int b200rt_debug_hidden(int model, const int32_t* ids, const int32_t* lens, int 
     CUDA_TRY(cudaMalloc(&dlens, static_cast<size_t>(n_items) * 4));
     CUDA_TRY(cudaMemcpy(dids, ids, M * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(dlens, l.data(), static_cast<size_t>(n_items) * 4, cudaMemcpyHostToDevice));
+    if (!d.x32_dbg) CUDA_TRY(cudaMalloc(&d.x32_dbg, static_cast<size_t>(rt->cap_rows) * HIDDEN * 4));
     int rc = forward(d, *m, 0, dids, dlens, n_items, max_len, nullptr, d.compute, n_layers);
     if (rc) return rc;
     CUDA_TRY(cudaStreamSynchronize(d.compute));
-    CUDA_TRY(cudaMemcpy(hidden_out, d.x32, M * HIDDEN * 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(hidden_out, d.x32_dbg, M * HIDDEN * 4, cudaMemcpyDeviceToHost));
     cudaFree(dids); cudaFree(dlens);
     return 0;
 }

@@ -12,8 +12,9 @@
 // lines per warp instruction (32 L1 wavefronts), which made the fp32 residual epilogue LSU-bound.  Instead
 // each column half of the tile (4 warps, thread = row) works on 128-row x 128-byte staging buffers in
 // shared memory (128B-swizzled, so a thread's 16-byte accesses are bank-conflict free per quarter warp):
-//   EPI_BIAS_RES_F32 : a DMA thread TMA-loads the fp32 residual chunk [128 x 32] into the buffer, the
-//                      compute threads add accumulator + bias in place, the DMA thread TMA-stores it to y.
+//   EPI_BIAS_RES_F32 : a DMA thread TMA-loads the fp32 PRE-LayerNorm residual chunk [128 x 32] of y into the
+//                      buffer, the compute threads re-apply that LayerNorm from the row's (mean, rstd) and
+//                      add accumulator + bias in place, the DMA thread TMA-stores the chunk back to y.
 //   EPI_BIAS(_GELU)_F16 : compute threads write fp16 [128 x 64] chunks, the DMA thread TMA-stores them.
 //
 //   full[s]   (leader's)  : leader producer arrive.expect_tx(64 KB); both CTAs' TMA loads complete_tx on it
@@ -39,8 +40,8 @@ constexpr int B_BYTES = (BN / 2) * BK * 2;      // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 32 KB per CTA
 constexpr int EBUF_BYTES = 128 * 128;           // one staging buffer: 128 rows x 128 bytes
 constexpr int OFF_EBUF = STAGES * STAGE_BYTES;  // [2 halves][2 buffers]
-constexpr int OFF_BIAS = OFF_EBUF + 4 * EBUF_BYTES;  // float [2 parities][256]
-constexpr int OFF_BAR = OFF_BIAS + 2 * 256 * 4;
+constexpr int OFF_BIAS = OFF_EBUF + 4 * EBUF_BYTES;  // float [2 parities][3: bias, gamma, beta][256]
+constexpr int OFF_BAR = OFF_BIAS + 2 * 3 * 256 * 4;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
@@ -63,8 +64,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
-                 const float* __restrict__ bias, int M, int N, int K, int dbg_mode) {
+                 const __grid_constant__ CUtensorMap tma_out, const float* __restrict__ bias, const float2* __restrict__ ln_stats,
+                 const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, int M, int N, int K, int dbg_mode) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -96,7 +97,6 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         prefetch_tmap(&tma_a);
         prefetch_tmap(&tma_b);
         prefetch_tmap(&tma_out);
-        if (EPI == EPI_BIAS_RES_F32) prefetch_tmap(&tma_res);
     }
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < STAGES; ++s) {
@@ -196,7 +196,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     int c0, c1;
                     coords(g, c0, c1);
                     mbar_arrive_expect_tx(&rfull[h * 2 + b], EBUF_BYTES);
-                    tma_load_2d(ebuf + b * EBUF_BYTES, &tma_res, &rfull[h * 2 + b], c0, c1);
+                    tma_load_2d(ebuf + b * EBUF_BYTES, &tma_out, &rfull[h * 2 + b], c0, c1);  // pre-LN residual, in place
                 } else {
                     mbar_arrive(&rfull[h * 2 + b]);  // nothing to load: just "buffer is free"
                 }
@@ -231,8 +231,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int tile = pair; tile < num_tiles; tile += num_pairs, tpar ^= 1) {
             const int n_blk = tile % num_n;
             // stage this tile's bias slice (128 floats per half) once; double buffered across tiles
-            const uint32_t sb = smem_u32(sbias + tpar * 256 + h * 128);
+            const uint32_t sb = smem_u32(sbias + tpar * 768 + h * 128);  // bias; gamma at +256 floats, beta at +512
             sts32f(sb + r * 4, __ldg(bias + n_blk * BN + h * (BN / 2) + r));
+            float ln_mean = 0.f, ln_rstd = 1.f;
+            if constexpr (EPI == EPI_BIAS_RES_F32) {
+                const bool has_ln = ln_stats != nullptr;
+                sts32f(sb + 1024 + r * 4, has_ln ? __ldg(ln_gamma + n_blk * BN + h * (BN / 2) + r) : 1.0f);
+                sts32f(sb + 2048 + r * 4, has_ln ? __ldg(ln_beta + n_blk * BN + h * (BN / 2) + r) : 0.0f);
+                if (has_ln) {
+                    const int grow = (tile / num_n) * (2 * BM) + cta_rank * BM + r;
+                    const float2 st = __ldg(ln_stats + grow);  // (mean, rstd) of this thread's row
+                    ln_mean = st.x;
+                    ln_rstd = st.y;
+                }
+            }
             named_bar_sync(1 + h, 128);
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
@@ -259,9 +271,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const uint32_t p = row_ptr + ((static_cast<uint32_t>(q) ^ swz) << 4);
-                        const float4 rs = lds128f(p);
-                        sts128f(p, __uint_as_float(acc[4 * q]) + bv[4 * q] + rs.x, __uint_as_float(acc[4 * q + 1]) + bv[4 * q + 1] + rs.y,
-                                __uint_as_float(acc[4 * q + 2]) + bv[4 * q + 2] + rs.z, __uint_as_float(acc[4 * q + 3]) + bv[4 * q + 3] + rs.w);
+                        const float4 y = lds128f(p);  // pre-LN residual
+                        const float4 gm = lds128f(sb + 1024 + (c * 32 + 4 * q) * 4);
+                        const float4 bt = lds128f(sb + 2048 + (c * 32 + 4 * q) * 4);
+                        // LN(y) with exactly ln_kernel's operations: fmaf((y - mean) * rstd, gamma, beta)
+                        const float r0 = fmaf((y.x - ln_mean) * ln_rstd, gm.x, bt.x), r1 = fmaf((y.y - ln_mean) * ln_rstd, gm.y, bt.y);
+                        const float r2 = fmaf((y.z - ln_mean) * ln_rstd, gm.z, bt.z), r3 = fmaf((y.w - ln_mean) * ln_rstd, gm.w, bt.w);
+                        sts128f(p, __uint_as_float(acc[4 * q]) + bv[4 * q] + r0, __uint_as_float(acc[4 * q + 1]) + bv[4 * q + 1] + r1,
+                                __uint_as_float(acc[4 * q + 2]) + bv[4 * q + 2] + r2, __uint_as_float(acc[4 * q + 3]) + bv[4 * q + 3] + r3);
                     }
                     fence_proxy_async_smem();
                     mbar_arrive(&cdone[h * 2 + b]);
@@ -311,12 +328,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 }  // namespace gemm
 
 template <int EPI>
-static cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tres,
+static cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const LnRef& ln,
                                const float* bias, int M, int N, int K, int sm_count, cudaStream_t stream, int dbg_mode) {
     const int tiles = ((M + 2 * gemm::BM - 1) / (2 * gemm::BM)) * (N / gemm::BN);
     int pairs = sm_count / 2;
     if (tiles < pairs) pairs = tiles;
-    gemm::gemm_pair_kernel<EPI><<<2 * pairs, gemm::NUM_THREADS, gemm::SMEM_BYTES, stream>>>(ta, tb, tout, tres, bias, M, N, K, dbg_mode);
+    gemm::gemm_pair_kernel<EPI><<<2 * pairs, gemm::NUM_THREADS, gemm::SMEM_BYTES, stream>>>(ta, tb, tout, bias, ln.stats, ln.gamma, ln.beta, M, N, K, dbg_mode);
     return cudaGetLastError();
 }
 
@@ -331,17 +348,17 @@ cudaError_t gemm_init_device() {
 
 // Bits 8+ of `epi` select a diagnostic mode (low nibble: 1 = no TMA loads, 2 = no MMA; high nibble: ring
 // length) used only by tools/gemm_diag.py.
-cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap* tres,
+cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const LnRef* ln,
                         const float* bias, int M, int N, int K, int sm_count, cudaStream_t stream) {
     const int dbg_mode = epi >> 8;
     epi &= 0xFF;
     if (N % gemm::BN != 0 || K % gemm::BK != 0 || M <= 0) return cudaErrorInvalidValue;
-    if (epi == EPI_BIAS_RES_F32 && !tres) return cudaErrorInvalidValue;
-    const CUtensorMap& tr = tres ? *tres : tout;
+    const LnRef none{nullptr, nullptr, nullptr};
+    const LnRef& l = ln ? *ln : none;
     switch (epi) {
-        case EPI_BIAS_F16: return launch_pair<EPI_BIAS_F16>(ta, tb, tout, tr, bias, M, N, K, sm_count, stream, dbg_mode);
-        case EPI_BIAS_GELU_F16: return launch_pair<EPI_BIAS_GELU_F16>(ta, tb, tout, tr, bias, M, N, K, sm_count, stream, dbg_mode);
-        case EPI_BIAS_RES_F32: return launch_pair<EPI_BIAS_RES_F32>(ta, tb, tout, tr, bias, M, N, K, sm_count, stream, dbg_mode);
+        case EPI_BIAS_F16: return launch_pair<EPI_BIAS_F16>(ta, tb, tout, l, bias, M, N, K, sm_count, stream, dbg_mode);
+        case EPI_BIAS_GELU_F16: return launch_pair<EPI_BIAS_GELU_F16>(ta, tb, tout, l, bias, M, N, K, sm_count, stream, dbg_mode);
+        case EPI_BIAS_RES_F32: return launch_pair<EPI_BIAS_RES_F32>(ta, tb, tout, l, bias, M, N, K, sm_count, stream, dbg_mode);
     }
     return cudaErrorInvalidValue;
 }

@@ -10,7 +10,8 @@ namespace b200 {
 enum GemmEpilogue : int {
     EPI_BIAS_F16 = 0,       // out fp16 = acc + bias                      (fused QKV projection)
     EPI_BIAS_GELU_F16 = 1,  // out fp16 = gelu_erf(acc + bias)            (FFN up-projection)
-    EPI_BIAS_RES_F32 = 2,   // out fp32 = acc + bias + resid (fp32)       (attention-out / FFN down)
+    EPI_BIAS_RES_F32 = 2,   // y fp32 (in place) = acc + bias + LN(y)     (attention-out / FFN down); LN(y) =
+                            //   (y - mean) * rstd * gamma + beta from the row statistics of the previous LayerNorm
 };
 
 constexpr int HIDDEN = 768;
@@ -24,9 +25,16 @@ cudaError_t kernels_init_device();
 // C[M,N] = epi(A[M,K] . W[N,K]^T + bias) on CTA pairs.  All operands move by TMA (128B swizzle):
 //   ta  : fp16 A   {K, rows>=M}  box {64,128}        tb  : fp16 W {K, N} box {64,128}
 //   tout: fp16 out {N, rows} box {64,128} (EPI 0/1)  or  fp32 out {N, rows} box {32,128} (EPI 2)
-//   tres: fp32 residual {N, rows} box {32,128} (EPI 2 only, else NULL).  rows must cover ceil(M/256)*256
-//         or the maps' own bounds clip the tail.  N % 256 == 0, K % 64 == 0.
-cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap* tres,
+//   EPI 2 reads the pre-LN residual through the same map `tout` (in place) and needs `ln`: the statistics and
+//         affine of the LayerNorm that produced this GEMM's residual input (NULL for EPI 0/1).  With ln.stats ==
+//         NULL the residual is added as is (plain `out += acc + bias`, used by the kernel-level tests).
+//   N % 256 == 0, K % 64 == 0; rows past M are clipped by the maps' own bounds.
+struct LnRef {
+    const float2* stats;  // [rows] (mean, rstd)
+    const float* gamma;   // [N]
+    const float* beta;    // [N]
+};
+cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const LnRef* ln,
                         const float* bias, int M, int N, int K, int sm_count, cudaStream_t stream);
 
 // Multi-head self-attention over a padded batch: qkv fp16 [B, S, 2304] (Q | K | V, head-major within each),
@@ -35,14 +43,15 @@ cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
 cudaError_t launch_attention(const CUtensorMap& tq, const int32_t* lens, __half* ctx, int B, int S,
                              cudaStream_t stream, unsigned long long* dbg = nullptr);
 
-// word + position + token_type(0) embedding gather, LayerNorm -> x32 (fp32 residual stream) and x16 (GEMM input)
+// word + position + token_type(0) embedding gather -> y32 (fp32 pre-LN sum = residual stream), LayerNorm ->
+// x16 (GEMM operand) + stats (mean, rstd per row).  x32_dbg (tests only, else NULL): normalised fp32 rows.
 cudaError_t launch_embed_ln(const int32_t* ids, const float* word, const float* pos, const float* type0,
-                            const float* gamma, const float* beta, float* x32, __half* x16, int n_tokens, int S,
-                            int vocab, float eps, cudaStream_t stream);
+                            const float* gamma, const float* beta, float* y32, __half* x16, float2* stats, float* x32_dbg,
+                            int n_tokens, int S, int vocab, float eps, cudaStream_t stream);
 
-// LayerNorm over rows of y (fp32 pre-LN sum) -> x32, x16
-cudaError_t launch_ln(const float* y, const float* gamma, const float* beta, float* x32, __half* x16, int n_rows,
-                      float eps, cudaStream_t stream);
+// LayerNorm over rows of y (fp32 pre-LN sum) -> x16 + stats; x32_dbg as above
+cudaError_t launch_ln(const float* y, const float* gamma, const float* beta, __half* x16, float2* stats, float* x32_dbg,
+                      int n_rows, float eps, cudaStream_t stream);
 
 // final LayerNorm of the CLS row of every item + L2 normalise; row i is stored at out + (out_row0 + i) * 768,
 // where `out` may be a peer-mapped pointer into the root GPU's gather buffer (the fused gather).

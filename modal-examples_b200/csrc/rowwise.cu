@@ -5,6 +5,11 @@
 // All of them: one warp per 768-wide row, 128-bit loads/stores (6 float4 per lane), statistics by
 // warp shuffle in fp32, two-pass variance on register-resident data (no E[x^2]-E[x]^2 cancellation).
 //
+// The fp32 residual stream is stored PRE-LayerNorm (y32) together with per-row (mean, rstd): the LayerNorm
+// kernels write only the fp16 GEMM operand (x16) and the statistics (4.5 KB/row of traffic instead of 7.5),
+// and the next residual-adding GEMM epilogue re-applies (y - mean) * rstd * gamma + beta with the very same
+// fp32 operations, so the normalised fp32 row is bit-identical to the one a materialising kernel would write.
+//
 // Restates BertEmbeddings.forward (HF modeling_bert.py:72-111), the LayerNorm halves of
 // BertSelfOutput :287-298 / BertOutput :345-356, and sentence-transformers' CLS pooling + Normalize
 // (reference 06_gpu_and_ml/gpu_snapshot.py:58, `normalize_embeddings=True`).
@@ -24,9 +29,9 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// normalise the 24 register-resident values of this lane; returns nothing, writes in place
-__device__ __forceinline__ void ln_inplace(float4 (&x)[V4], const float* __restrict__ gamma,
-                                           const float* __restrict__ beta, float eps, int lane) {
+// normalise the 24 register-resident values of this lane in place; returns (mean, rstd) of the row
+__device__ __forceinline__ float2 ln_inplace(float4 (&x)[V4], const float* __restrict__ gamma,
+                                             const float* __restrict__ beta, float eps, int lane) {
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < V4; ++i) s += (x[i].x + x[i].y) + (x[i].z + x[i].w);
@@ -49,23 +54,27 @@ __device__ __forceinline__ void ln_inplace(float4 (&x)[V4], const float* __restr
         x[i].z = fmaf(x[i].z * rstd, g.z, b.z);
         x[i].w = fmaf(x[i].w * rstd, g.w, b.w);
     }
+    return make_float2(mean, rstd);
 }
 
+// fp16 copy of the normalised row (the GEMM operand); x32 only for the debug materialisation
 __device__ __forceinline__ void store_row(const float4 (&x)[V4], float* __restrict__ x32, __half* __restrict__ x16,
                                           size_t row, int lane) {
-    float4* o32 = reinterpret_cast<float4*>(x32 + row * H);
     uint2* o16 = reinterpret_cast<uint2*>(x16 + row * H);
 #pragma unroll
-    for (int i = 0; i < V4; ++i) {
-        o32[i * 32 + lane] = x[i];
-        o16[i * 32 + lane] = make_uint2(pack_half2(x[i].x, x[i].y), pack_half2(x[i].z, x[i].w));
+    for (int i = 0; i < V4; ++i) o16[i * 32 + lane] = make_uint2(pack_half2(x[i].x, x[i].y), pack_half2(x[i].z, x[i].w));
+    if (x32 != nullptr) {
+        float4* o32 = reinterpret_cast<float4*>(x32 + row * H);
+#pragma unroll
+        for (int i = 0; i < V4; ++i) o32[i * 32 + lane] = x[i];
     }
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 embed_ln_kernel(const int32_t* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ pos,
                 const float* __restrict__ type0, const float* __restrict__ gamma, const float* __restrict__ beta,
-                float* __restrict__ x32, __half* __restrict__ x16, int n_tokens, int S, int vocab, float eps) {
+                float* __restrict__ y32, __half* __restrict__ x16, float2* __restrict__ stats, float* __restrict__ x32_dbg,
+                int n_tokens, int S, int vocab, float eps) {
     const int lane = threadIdx.x & 31;
     const int tok = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (tok >= n_tokens) return;
@@ -84,13 +93,18 @@ embed_ln_kernel(const int32_t* __restrict__ ids, const float* __restrict__ word,
         // HF order: (word + token_type) + position
         x[i] = make_float4((a.x + c.x) + b.x, (a.y + c.y) + b.y, (a.z + c.z) + b.z, (a.w + c.w) + b.w);
     }
-    ln_inplace(x, gamma, beta, eps, lane);
-    store_row(x, x32, x16, tok, lane);
+    // the residual stream is kept PRE-LayerNorm (y32) plus per-row (mean, rstd); consumers re-apply the affine
+    float4* y4 = reinterpret_cast<float4*>(y32 + static_cast<size_t>(tok) * H);
+#pragma unroll
+    for (int i = 0; i < V4; ++i) y4[i * 32 + lane] = x[i];
+    const float2 st = ln_inplace(x, gamma, beta, eps, lane);
+    if (lane == 0) stats[tok] = st;
+    store_row(x, x32_dbg, x16, tok, lane);
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 ln_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
-          float* __restrict__ x32, __half* __restrict__ x16, int n_rows, float eps) {
+          __half* __restrict__ x16, float2* __restrict__ stats, float* __restrict__ x32_dbg, int n_rows, float eps) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (row >= n_rows) return;
@@ -98,8 +112,9 @@ ln_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const fl
     float4 x[V4];
 #pragma unroll
     for (int i = 0; i < V4; ++i) x[i] = y4[i * 32 + lane];
-    ln_inplace(x, gamma, beta, eps, lane);
-    store_row(x, x32, x16, row, lane);
+    const float2 st = ln_inplace(x, gamma, beta, eps, lane);
+    if (lane == 0) stats[row] = st;
+    store_row(x, x32_dbg, x16, row, lane);
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
@@ -158,18 +173,18 @@ scatter_kernel(const int32_t* __restrict__ src_ids, const int32_t* __restrict__ 
 }  // namespace rw
 
 cudaError_t launch_embed_ln(const int32_t* ids, const float* word, const float* pos, const float* type0,
-                            const float* gamma, const float* beta, float* x32, __half* x16, int n_tokens, int S,
-                            int vocab, float eps, cudaStream_t stream) {
+                            const float* gamma, const float* beta, float* y32, __half* x16, float2* stats, float* x32_dbg,
+                            int n_tokens, int S, int vocab, float eps, cudaStream_t stream) {
     const int grid = (n_tokens + rw::WARPS_PER_BLOCK - 1) / rw::WARPS_PER_BLOCK;
-    rw::embed_ln_kernel<<<grid, rw::WARPS_PER_BLOCK * 32, 0, stream>>>(ids, word, pos, type0, gamma, beta, x32, x16,
-                                                                       n_tokens, S, vocab, eps);
+    rw::embed_ln_kernel<<<grid, rw::WARPS_PER_BLOCK * 32, 0, stream>>>(ids, word, pos, type0, gamma, beta, y32, x16, stats,
+                                                                       x32_dbg, n_tokens, S, vocab, eps);
     return cudaGetLastError();
 }
 
-cudaError_t launch_ln(const float* y, const float* gamma, const float* beta, float* x32, __half* x16, int n_rows,
-                      float eps, cudaStream_t stream) {
+cudaError_t launch_ln(const float* y, const float* gamma, const float* beta, __half* x16, float2* stats, float* x32_dbg,
+                      int n_rows, float eps, cudaStream_t stream) {
     const int grid = (n_rows + rw::WARPS_PER_BLOCK - 1) / rw::WARPS_PER_BLOCK;
-    rw::ln_kernel<<<grid, rw::WARPS_PER_BLOCK * 32, 0, stream>>>(y, gamma, beta, x32, x16, n_rows, eps);
+    rw::ln_kernel<<<grid, rw::WARPS_PER_BLOCK * 32, 0, stream>>>(y, gamma, beta, x16, stats, x32_dbg, n_rows, eps);
     return cudaGetLastError();
 }
 
