@@ -62,7 +62,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
     uint64_t* o_full = bars + 14;     // [m][4]  O_c landed in slot c&3
     uint64_t* slot_free = bars + 22;  // [m][4]  O_c has been folded into the registers
     uint64_t* p_full = bars + 30;     // [m][2]
-    uint64_t* p_empty = bars + 34;    // [m][2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
 
     const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
@@ -89,7 +88,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
             }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&p_full[m * 2 + i], 128);
-                mbar_init(&p_empty[m * 2 + i], 1);
             }
         }
         fence_barrier_init();
@@ -164,7 +162,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
                     const uint32_t bv = v_addr + (sb * SB + kk * 16) * 128;  // key row -> 128 B
                     umma_f16_ss(tm + slot * SB, make_sw128_desc(a), make_sw128_desc(bv), idesc_o, kk != 0);
                 }
-                umma_commit(&p_empty[m * 2 + ps]);
                 umma_commit(&o_full[m * 4 + slot]);
                 ATT_STAMP(2 + m, c, 2);
                 if (c + 2 < total) issue_s(c + 2);
@@ -187,15 +184,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
             float m_run = -INFINITY, l_run = 0.f;
             float mq[2] = {0.f, 0.f}, lq[2] = {0.f, 0.f};  // (m, l) of the two sub-blocks not yet folded
             // fold sub-block cj (its O is in slot cj&3) into the running state and free the slot
-            auto fold = [&](uint32_t cj, float m_j, float l_j) {
+            // `need_wait`: in the steady state O_cj is already known to be complete (see the s_full note below)
+            auto fold = [&](uint32_t cj, float m_j, float l_j, bool need_wait) {
                 const float m_new = fmaxf(m_run, m_j);
                 const float sc = ex2_approx((m_run - m_new) * kScaleLog2e);  // 0 for the tile's first sub-block
                 const float w = ex2_approx((m_j - m_new) * kScaleLog2e);
                 l_run = fmaf(w, l_j, l_run * sc);
                 m_run = m_new;
                 const uint32_t slot = cj & 3;
-                mbar_wait(&o_full[m * 4 + slot], (cj >> 2) & 1);
-                tc_fence_after();
+                if (need_wait) {
+                    mbar_wait(&o_full[m * 4 + slot], (cj >> 2) & 1);
+                    tc_fence_after();
+                }
 #pragma unroll
                 for (int half = 0; half < D / 32; ++half) {
                     uint32_t o[32];
@@ -211,6 +211,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
             for (int sb = 0; sb < nsb; ++sb, ++c) {
                 const uint32_t slot = c & 3, ps = c & 1;
                 if (obs) ATT_STAMP(m, c, 0);
+                // The MMA thread issues PV_{c-2} before S_c and tcgen05.commit arrives only when ALL its earlier MMAs have
+                // retired, so s_full(c) also tells us that O_{c-2} is complete and that P slot c&1 has been consumed:
+                // one barrier wait per sub-block instead of three (each costs ~150-190 cycles even when already complete).
                 mbar_wait(&s_full[m * 4 + slot], (c >> 2) & 1);
                 tc_fence_after();
                 if (obs) ATT_STAMP(m, c, 1);
@@ -231,8 +234,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
                     }
                 }
                 const float neg_ms = -mx * kScaleLog2e;
-                if (obs) ATT_STAMP(m, c, 2);
-                mbar_wait(&p_empty[m * 2 + ps], ((c >> 1) & 1) ^ 1);
                 if (obs) ATT_STAMP(m, c, 3);
                 float ls0 = 0.f, ls1 = 0.f;
                 const uint32_t row_ptr = p_base + ps * TILE_BYTES + r * 128;
@@ -254,14 +255,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
                 fence_proxy_async_smem();  // P_c visible to the tensor core's async-proxy reads
                 mbar_arrive(&p_full[m * 2 + ps]);
                 if (obs) ATT_STAMP(m, c, 4);
-                if (sb >= 2) fold(c - 2, mq[sb & 1], lq[sb & 1]);
+                if (sb >= 2) fold(c - 2, mq[sb & 1], lq[sb & 1], false);
                 if (obs) ATT_STAMP(m, c, 5);
                 mq[sb & 1] = mx;
                 lq[sb & 1] = ls0 + ls1;
             }
             // drain the (up to) two sub-blocks still in flight
-            if (nsb >= 2) fold(c - 2, mq[nsb & 1], lq[nsb & 1]);
-            fold(c - 1, mq[(nsb - 1) & 1], lq[(nsb - 1) & 1]);
+            if (nsb >= 2) fold(c - 2, mq[nsb & 1], lq[nsb & 1], true);
+            fold(c - 1, mq[(nsb - 1) & 1], lq[(nsb - 1) & 1], true);
             if (obs) ATT_STAMP(m, c - 1, 6);
             const float inv_l = 1.0f / l_run;
             const int q_row = qt * QT + r;
