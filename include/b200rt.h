@@ -38,7 +38,8 @@ typedef struct b200rt_stats_t {
     uint64_t kernel_launches;           /* of this library's own kernels */
     uint64_t h2d_bytes, d2h_bytes;      /* through submit()/wait() */
     uint64_t peer_bytes;                /* scatter + fused-gather bytes that crossed NVLink */
-    double stage_us, h2d_scatter_us, forward_us, d2h_us; /* summed per-wave stage times (device events) */
+    double stage_us, h2d_scatter_us, forward_us, d2h_us; /* summed per-wave stage times (device events; forward = root replica) */
+    double gap_us;                      /* idle time of the root's compute stream between consecutive waves */
 } b200rt_stats_t;
 
 /* Replica pool.  Stands in for `@app.cls(gpu=..., max_containers=N)` + `@modal.concurrent`

@@ -19,6 +19,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <unordered_map>
 #include <vector>
 
@@ -164,6 +165,7 @@ struct Dev {
     int32_t* ids_in[NSLOT] = {nullptr, nullptr, nullptr};
     int32_t* lens_in[NSLOT] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_done[NSLOT];
+    cudaEvent_t ev_begin[NSLOT], ev_end[NSLOT];  // timing: the forward itself on this replica's compute stream
     std::mutex mu;  // serialises host-side enqueue on this replica (scheduler vs. embed_device/debug)
 };
 
@@ -216,6 +218,7 @@ struct Runtime {
     bool stopping = false;
     std::thread dispatcher, completer;
     b200rt_stats_t stats{};
+    int last_end_slot = -1;  // completer only
     std::mutex stats_mu;
     std::string async_error;
 };
@@ -245,8 +248,8 @@ int get_qkv_map(Dev& d, int S, const CUtensorMap** out) {
 
 // Enqueue the forward of one padded batch [B, S] on `stream`.  out: fp32 [B, 768], may be peer memory.
 // n_layers >= 0 (debug): stop early and materialise the post-LN hidden state in d.x32_dbg.
-int forward(Dev& d, const Model& m, int dev_index, const int32_t* ids, const int32_t* lens, int B, int S, float* out,
-            cudaStream_t stream, int n_layers = -1, Prof* prof = nullptr, uint64_t* launches = nullptr) {
+int forward_enqueue(Dev& d, const Model& m, int dev_index, const int32_t* ids, const int32_t* lens, int B, int S, float* out,
+                    cudaStream_t stream, int n_layers = -1, Prof* prof = nullptr, uint64_t* launches = nullptr) {
     const DevWeights& w = m.per_dev[dev_index];
     const b200rt_bert_config& c = m.cfg;
     const int L = n_layers < 0 ? c.layers : n_layers;
@@ -297,6 +300,64 @@ int forward(Dev& d, const Model& m, int dev_index, const int32_t* ids, const int
         ++nl; mark("pool_normalize");
     }
     if (launches) *launches += nl;
+    return 0;
+}
+
+// Small batches are launch-bound (a single 512-token item is ~85 launches of 5-40 us kernels): below
+// GRAPH_MAX_ROWS rows the launch sequence is captured once per (buffers, shape) into a CUDA graph and replayed.
+// Large waves keep plain launches (their kernels are long enough to hide the launch cost, and graphs per shape would
+// only add memory).  The caller holds d.mu.
+constexpr int GRAPH_MAX_ROWS = 8192;
+constexpr size_t GRAPH_CACHE_MAX = 96;
+
+struct GraphKey {
+    const void *model, *ids, *lens, *out;
+    cudaStream_t stream;
+    int B, S;
+    bool operator<(const GraphKey& o) const {
+        return std::tie(model, ids, lens, out, stream, B, S) < std::tie(o.model, o.ids, o.lens, o.out, o.stream, o.B, o.S);
+    }
+};
+struct GraphEntry {
+    cudaGraphExec_t exec;
+    uint64_t launches;
+};
+std::map<GraphKey, GraphEntry>& graph_cache(Dev& d) {
+    static std::mutex mu;
+    static std::map<Dev*, std::map<GraphKey, GraphEntry>> all;
+    std::lock_guard<std::mutex> lk(mu);
+    return all[&d];
+}
+
+int forward(Dev& d, const Model& m, int dev_index, const int32_t* ids, const int32_t* lens, int B, int S, float* out,
+            cudaStream_t stream, int n_layers = -1, Prof* prof = nullptr, uint64_t* launches = nullptr) {
+    static const bool no_graphs = getenv("B200RT_NO_GRAPHS") != nullptr;
+    if (n_layers >= 0 || prof || B * S > GRAPH_MAX_ROWS || no_graphs)
+        return forward_enqueue(d, m, dev_index, ids, lens, B, S, out, stream, n_layers, prof, launches);
+    auto& cache = graph_cache(d);
+    const GraphKey key{&m, ids, lens, out, stream, B, S};
+    auto it = cache.find(key);
+    if (it == cache.end()) {
+        if (cache.size() >= GRAPH_CACHE_MAX) return forward_enqueue(d, m, dev_index, ids, lens, B, S, out, stream, -1, nullptr, launches);
+        const CUtensorMap* mq = nullptr;
+        if (int rc = get_qkv_map(d, S, &mq)) return rc;  // host-side map creation happens outside the capture
+        uint64_t nl = 0;
+        CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = forward_enqueue(d, m, dev_index, ids, lens, B, S, out, stream, -1, nullptr, &nl);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        CUDA_TRY(ce);
+        GraphEntry ent{nullptr, nl};
+        CUDA_TRY(cudaGraphInstantiate(&ent.exec, graph, 0));
+        cudaGraphDestroy(graph);
+        it = cache.emplace(key, ent).first;
+    }
+    CUDA_TRY(cudaGraphLaunch(it->second.exec, stream));
+    if (launches) *launches += it->second.launches;
     return 0;
 }
 
@@ -401,6 +462,7 @@ void dispatcher_main(Runtime* rtp) {
             std::lock_guard<std::mutex> dl(d.mu);
             SCHED_TRY(cudaSetDevice(d.id));
             SCHED_TRY(cudaStreamWaitEvent(d.compute, rt.ev_scatter[slot], 0));
+            SCHED_TRY(cudaEventRecord(d.ev_begin[slot], d.compute));
             float* dst = rt.d_out_gather[slot] + static_cast<size_t>(plan.item_begin[g]) * HIDDEN;
             int rc = forward(d, model, g, d.ids_in[slot], d.lens_in[slot], plan.item_count[g], S, dst, d.compute, -1,
                              nullptr, &launches);
@@ -408,6 +470,7 @@ void dispatcher_main(Runtime* rtp) {
                 fail_all(rt, t_last_error);
                 return;
             }
+            SCHED_TRY(cudaEventRecord(d.ev_end[slot], d.compute));
             SCHED_TRY(cudaEventRecord(d.ev_done[slot], d.compute));
         }
         SCHED_TRY(cudaSetDevice(root.id));
@@ -457,7 +520,13 @@ void completer_main(Runtime* rtp) {
         }
         float ms_in = 0, ms_fwd = 0, ms_out = 0;
         cudaEventElapsedTime(&ms_in, rt.ev_t0[slot], rt.ev_scatter[slot]);
-        cudaEventElapsedTime(&ms_fwd, rt.ev_scatter[slot], rt.ev_fwd_end[slot]);
+        cudaEventElapsedTime(&ms_fwd, rt.devs[0]->ev_begin[slot], rt.devs[0]->ev_end[slot]);  // root replica's forward
+        float ms_gap = 0;
+        if (rt.last_end_slot >= 0 && cudaEventElapsedTime(&ms_gap, rt.devs[0]->ev_end[rt.last_end_slot], rt.devs[0]->ev_begin[slot]) != cudaSuccess) {
+            ms_gap = 0;
+            cudaGetLastError();
+        }
+        rt.last_end_slot = slot;
         cudaEventElapsedTime(&ms_out, rt.ev_fwd_end[slot], rt.ev_wave[slot]);
         for (const Segment& sg : wv.segs)
             memcpy(sg.t->out + static_cast<size_t>(sg.ticket_off) * HIDDEN,
@@ -468,6 +537,7 @@ void completer_main(Runtime* rtp) {
             rt.stats.waves++;
             rt.stats.h2d_scatter_us += ms_in * 1e3;
             rt.stats.forward_us += ms_fwd * 1e3;
+            rt.stats.gap_us += (ms_gap > 0 ? ms_gap : 0) * 1e3;
             rt.stats.d2h_us += ms_out * 1e3;
         }
         {
@@ -517,6 +587,8 @@ int alloc_dev(Runtime& rt, Dev& d) {
         CUDA_TRY(cudaMalloc(&d.lens_in[s], R * 4));
         CUDA_TRY(cudaMemset(d.ids_in[s], 0, R * 4));
         CUDA_TRY(cudaEventCreateWithFlags(&d.ev_done[s], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreate(&d.ev_begin[s]));
+        CUDA_TRY(cudaEventCreate(&d.ev_end[s]));
     }
     return 0;
 }
@@ -890,7 +962,7 @@ void b200rt_shutdown(void) {
     for (auto& d : rt->devs) {
         cudaSetDevice(d->id);
         cudaFree(d->x32_dbg); cudaFree(d->stats); cudaFree(d->y32); cudaFree(d->x16); cudaFree(d->qkv); cudaFree(d->ctx); cudaFree(d->ffn);
-        for (int s = 0; s < NSLOT; ++s) { cudaFree(d->ids_in[s]); cudaFree(d->lens_in[s]); cudaEventDestroy(d->ev_done[s]); }
+        for (int s = 0; s < NSLOT; ++s) { cudaFree(d->ids_in[s]); cudaFree(d->lens_in[s]); cudaEventDestroy(d->ev_done[s]); cudaEventDestroy(d->ev_begin[s]); cudaEventDestroy(d->ev_end[s]); }
         cudaStreamDestroy(d->compute);
     }
     cudaSetDevice(rt->devs[0]->id);
