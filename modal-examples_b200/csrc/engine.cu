@@ -322,11 +322,18 @@ struct GraphEntry {
     cudaGraphExec_t exec;
     uint64_t launches;
 };
+std::mutex g_graph_mu;
+std::map<Dev*, std::map<GraphKey, GraphEntry>> g_graphs;
 std::map<GraphKey, GraphEntry>& graph_cache(Dev& d) {
-    static std::mutex mu;
-    static std::map<Dev*, std::map<GraphKey, GraphEntry>> all;
-    std::lock_guard<std::mutex> lk(mu);
-    return all[&d];
+    std::lock_guard<std::mutex> lk(g_graph_mu);
+    return g_graphs[&d];
+}
+void drop_graphs(Dev& d) {  // the replica is going away: its cached launches point into freed buffers
+    std::lock_guard<std::mutex> lk(g_graph_mu);
+    auto it = g_graphs.find(&d);
+    if (it == g_graphs.end()) return;
+    for (auto& kv : it->second) cudaGraphExecDestroy(kv.second.exec);
+    g_graphs.erase(it);
 }
 
 int forward(Dev& d, const Model& m, int dev_index, const int32_t* ids, const int32_t* lens, int B, int S, float* out,
@@ -961,6 +968,7 @@ void b200rt_shutdown(void) {
         }
     for (auto& d : rt->devs) {
         cudaSetDevice(d->id);
+        drop_graphs(*d);
         cudaFree(d->x32_dbg); cudaFree(d->stats); cudaFree(d->y32); cudaFree(d->x16); cudaFree(d->qkv); cudaFree(d->ctx); cudaFree(d->ffn);
         for (int s = 0; s < NSLOT; ++s) { cudaFree(d->ids_in[s]); cudaFree(d->lens_in[s]); cudaEventDestroy(d->ev_done[s]); cudaEventDestroy(d->ev_begin[s]); cudaEventDestroy(d->ev_end[s]); }
         cudaStreamDestroy(d->compute);
