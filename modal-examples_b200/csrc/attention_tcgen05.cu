@@ -1,21 +1,27 @@
 // Multi-head self-attention for S <= 512, d = 64, on tcgen05 (sm_100a).
 //
 // One CTA per (item, head) keeps that head's K and V (<= 512 x 64 fp16 each) resident in shared memory and
-// runs TWO independent "machines" over the item's 128-row query tiles (machine m takes tiles m, m+2, ...).
-// A machine owns 256 TMEM columns organised as a ring of four 64-column slots, one Q buffer, a 2-slot P
-// ring, its own MMA-issuing thread and one softmax warpgroup (thread = query row).  Its work is a stream of
-// 64-key sub-blocks c = 0, 1, 2, ... (continuing across its tiles), software-pipelined per slot:
+// streams the item's 128-row query tiles through them as a sequence of 64-key sub-blocks c = 0, 1, 2, ...
+// (8 per 512-key tile, continuing across tiles).  The kernel is bound by instruction issue on the SM sub-partitions
+// that run the exp (tools/ubench/spin_cost.cu: a 64-score exp phase takes 660 cycles alone and 1100+ next to the FMAs
+// of an accumulator fold), so everything that is not the exp itself is kept off those sub-partitions' issue ports:
 //
-//   MMA thread : S_c = Q . K_c^T (128x64) into slot c&3, issued two sub-blocks ahead of the softmax
-//                O_c = P_c . V_c overwrites S_c's slot as soon as P_c is in shared memory
-//   softmax    : one pass over the 64 scores of its row in registers -> max m_c, P_c = exp2((S - m_c) k) as fp16
-//                into a 128B-swizzled smem tile, l_c = sum(P_c); then, lagging two sub-blocks behind, folds
-//                O_{c-2} into the running (max, sum, accumulator) in registers and frees the slot
-//   tile end   : ctx = acc / l
+//   TMEM         : two 64-column O accumulators (tile t -> t&1) + a ring of four 64-column S slots
+//   S thread     : S_c = Q . K_c^T (128x64) into S slot c&3, as far ahead as free slots allow
+//   P.V thread   : O_t += P_c . V_c accumulates IN TMEM across the tile's sub-blocks (no per-sub-block fold)
+//   2 exp WGs    : warpgroup w takes sub-blocks c = w (mod 2), thread = query row: one TMEM read of the 64 scores,
+//                  row max, P_c = exp2((S - m) k) as fp16 into its own 128B-swizzled smem tile, partial row sum.
+//                  m is the row's RUNNING reference maximum, handed from sub-block to sub-block through shared memory;
+//                  it only moves when the new maximum exceeds it by more than 2^8 in the exp2 domain (P <= 256 is exact
+//                  enough in fp16 and the sums are fp32), so the accumulator in TMEM is rescaled (tcgen05.ld/st by
+//                  the exp warp that saw the jump) a handful of times per tile instead of once per sub-block.
+//                  The exp phases of the two warpgroups take turns on the MUFU (named-barrier token).
+//   epilogue WG  : once per tile: l = sum of the warpgroups' partial sums brought to the final m, ctx = O / l as fp16
+//                  through a swizzled staging tile and one TMA store (row-per-thread global stores cost 32 LSU
+//                  wavefronts each and stalled the exp warps' shared-memory stores behind them)
 //
-// Every sub-block keeps its own (m, l, O): the accumulator in TMEM is never rescaled and the scores are
-// read exactly once.  Keys >= len are masked to -inf before the max (exactly P = 0, matching HF's additive
-// -inf mask); sub-blocks wholly past len are skipped.  k = log2(e) / sqrt(64).
+// Keys >= len are masked to -inf before the max (exactly P = 0, matching HF's additive -inf mask); sub-blocks wholly
+// past len are skipped.  k = log2(e) / sqrt(64).
 //
 // Restates BertSelfAttention.forward (HF modeling_bert.py:143-207) for the TEI /embed path the
 // reference calls at 06_gpu_and_ml/embeddings/text_embeddings_inference.py:100.
@@ -26,27 +32,41 @@ namespace b200 {
 namespace attn {
 
 constexpr int QT = 128;      // query rows per tile
-constexpr int KB = 128;      // keys per S block (one MMA chain)
-constexpr int SB = 64;       // keys per softmax / PV sub-block
+constexpr int KB = 128;      // keys per K/V smem tile (TMA box)
+constexpr int SB = 64;       // keys per sub-block
 constexpr int D = HEAD_DIM;  // 64
 constexpr int MAX_KB = 4;    // S <= 512
+constexpr int MAX_NQ = 4;
+constexpr int NSLOT = 4;     // TMEM S slots of 64 columns
+constexpr int NEXP = 2;      // exp warpgroups == P buffers
+constexpr bool USE_TOKEN = true;
+constexpr uint32_t TM_O = 0;            // 2 x 64 columns
+constexpr uint32_t TM_S = 2 * D;        // NSLOT x 64 columns
 constexpr int TILE_BYTES = 128 * D * 2;  // 16 KB: 128 rows x 128 B
-constexpr int OFF_Q = 0;                            // [2 machines] x 16 KB
+constexpr int OFF_Q = 0;                            // 2 x 16 KB (double buffered across tiles)
 constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;       // 4 x 16 KB
 constexpr int OFF_V = OFF_K + MAX_KB * TILE_BYTES;  // 4 x 16 KB
-constexpr int OFF_P = OFF_V + MAX_KB * TILE_BYTES;  // [2 machines][2 slots] x 16 KB
-constexpr int OFF_BAR = OFF_P + 4 * TILE_BYTES;
-constexpr int SMEM_BYTES = OFF_BAR + 384 + 1024;
-constexpr int NUM_THREADS = 128 + 256;
+constexpr int OFF_P = OFF_V + MAX_KB * TILE_BYTES;  // NEXP x 16 KB
+constexpr int OFF_O = OFF_P + NEXP * TILE_BYTES;    // 16 KB: the epilogue's staging tile for the TMA store
+constexpr int OFF_MR = OFF_O + TILE_BYTES;            // float [NEXP][128]: reference max after warpgroup w's latest sub-block
+constexpr int OFF_LS = OFF_MR + NEXP * QT * 4;      // float2 [MAX_NQ][NEXP][128]: (reference max, partial sum) per tile
+constexpr int OFF_BAR = OFF_LS + MAX_NQ * NEXP * QT * 8;
+constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+constexpr int NUM_THREADS = 128 + NEXP * 128 + 128;
+constexpr int BAR_TOKEN = 1;         // named barriers 1 .. NEXP: MUFU token
+constexpr int BAR_MAX = 1 + NEXP;    // named barriers 1+NEXP .. 2 NEXP: running-max hand-off
+constexpr int BAR_EPI = 1 + 2 * NEXP;  // the epilogue warpgroup's own barrier
 
 // softmax_scale * log2(e) with softmax_scale = 1/sqrt(64)
 constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;
+// the reference max follows the true max only when it is exceeded by more than this (raw score units): P <= 2^8
+constexpr float kRescaleThreshold = 8.0f / kScaleLog2e;
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restrict__ lens, __half* __restrict__ ctx,
-                 int S, unsigned long long* __restrict__ dbg) {
-    // dbg (diagnostics, normally NULL): CTA 0 records clock64() stamps; observer o in {softmax m0, softmax m1, mma m0,
-    // mma m1}, 32 sub-blocks x 8 slots each (tools/attn_timeline.py prints them)
+attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tctx,
+                 const int32_t* __restrict__ lens, int S, unsigned long long* __restrict__ dbg) {
+    // dbg (diagnostics, normally NULL): CTA 0 records clock64() stamps; observer o in {exp WG 0..2, epilogue WG, P.V thread},
+    // 32 sub-blocks x 8 slots each (tools/attn_timeline.py prints them)
 #define ATT_STAMP(o, c, slot)                                                                          \
     do {                                                                                               \
         if (dbg != nullptr && blockIdx.x == 0 && (c) < 32) dbg[((o) * 32 + (c)) * 8 + (slot)] = clock64(); \
@@ -56,13 +76,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* k_full = bars + 0;
     uint64_t* v_full = bars + 1;
-    uint64_t* q_full = bars + 2;      // [m]
-    uint64_t* q_empty = bars + 4;     // [m]
-    uint64_t* s_full = bars + 6;      // [m][4]  S_c landed in slot c&3
-    uint64_t* o_full = bars + 14;     // [m][4]  O_c landed in slot c&3
-    uint64_t* slot_free = bars + 22;  // [m][4]  O_c has been folded into the registers
-    uint64_t* p_full = bars + 30;     // [m][2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
+    uint64_t* q_full = bars + 2;       // [2]
+    uint64_t* q_empty = bars + 4;      // [2]
+    uint64_t* o_done = bars + 6;       // [2]  the tile's last P.V has retired
+    uint64_t* o_free = bars + 8;       // [2]  the epilogue has read the accumulator
+    uint64_t* s_full = bars + 10;      // [NSLOT]  S_c landed in slot c&3
+    uint64_t* s_free = bars + 14;      // [NSLOT]  S_c is in the exp warpgroup's registers
+    uint64_t* p_full = bars + 18;      // [NEXP]  P buffer w written
+    uint64_t* pv_done = bars + 22;     // [NEXP]  the P.V reading P buffer w has retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
     const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
     const int lane = lane_id();
@@ -71,24 +93,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
     int len = lens[b];
     len = len < 1 ? 1 : (len > S ? S : len);
     const int nq = (S + QT - 1) / QT;
-    const int nsb = (len + SB - 1) / SB;       // valid 64-key sub-blocks
-    const int nkb = (nsb + 1) / 2;             // 128-key blocks holding them
+    const int nsb = (len + SB - 1) / SB;  // valid 64-key sub-blocks per tile
+    const int nkb = (nsb + 1) / 2;        // 128-key K/V tiles holding them
+    const int total = nq * nsb;           // the CTA's stream of sub-blocks
 
-    if (warp == 0 && elect_one()) prefetch_tmap(&tq);
+    if (warp == 0 && elect_one()) {
+        prefetch_tmap(&tq);
+        prefetch_tmap(&tctx);
+    }
     if (warp == 1 && elect_one()) {
         mbar_init(k_full, 1);
         mbar_init(v_full, 1);
-        for (int m = 0; m < 2; ++m) {
-            mbar_init(&q_full[m], 1);
-            mbar_init(&q_empty[m], 1);
-            for (int i = 0; i < 4; ++i) {
-                mbar_init(&s_full[m * 4 + i], 1);
-                mbar_init(&o_full[m * 4 + i], 1);
-                mbar_init(&slot_free[m * 4 + i], 128);
-            }
-            for (int i = 0; i < 2; ++i) {
-                mbar_init(&p_full[m * 2 + i], 128);
-            }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&q_full[i], 1);
+            mbar_init(&q_empty[i], 1);
+            mbar_init(&o_done[i], 1);
+            mbar_init(&o_free[i], 128);
+        }
+        for (int i = 0; i < NSLOT; ++i) {
+            mbar_init(&s_full[i], 1);
+            mbar_init(&s_free[i], 128);
+        }
+        for (int i = 0; i < NEXP; ++i) {
+            mbar_init(&p_full[i], 128);
+            mbar_init(&pv_done[i], 1);
         }
         fence_barrier_init();
     }
@@ -101,9 +129,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
     if (warp == 0) {
         if (elect_one()) {
             // ------------------------------------------------------------ TMA producer
-            for (int qt = 0; qt < nq && qt < 2; ++qt) {
-                mbar_arrive_expect_tx(&q_full[qt], TILE_BYTES);
-                tma_load_3d(smem + OFF_Q + qt * TILE_BYTES, &tq, &q_full[qt], h * D, qt * QT, b);
+            for (int t = 0; t < nq && t < 2; ++t) {
+                mbar_arrive_expect_tx(&q_full[t], TILE_BYTES);
+                tma_load_3d(smem + OFF_Q + t * TILE_BYTES, &tq, &q_full[t], h * D, t * QT, b);
             }
             mbar_arrive_expect_tx(k_full, nkb * TILE_BYTES);
             for (int j = 0; j < nkb; ++j)
@@ -111,172 +139,244 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const int32_t* __restri
             mbar_arrive_expect_tx(v_full, nkb * TILE_BYTES);
             for (int j = 0; j < nkb; ++j)
                 tma_load_3d(smem + OFF_V + j * TILE_BYTES, &tq, v_full, 2 * HIDDEN + h * D, j * KB, b);
-            for (int qt = 2; qt < nq; ++qt) {
-                const int m = qt & 1, tl = qt >> 1;
-                mbar_wait(&q_empty[m], (tl - 1) & 1);
-                mbar_arrive_expect_tx(&q_full[m], TILE_BYTES);
-                tma_load_3d(smem + OFF_Q + m * TILE_BYTES, &tq, &q_full[m], h * D, qt * QT, b);
+            for (int t = 2; t < nq; ++t) {
+                const int qb = t & 1;
+                mbar_wait(&q_empty[qb], ((t >> 1) - 1) & 1);  // tile t-2's S MMAs have retired
+                mbar_arrive_expect_tx(&q_full[qb], TILE_BYTES);
+                tma_load_3d(smem + OFF_Q + qb * TILE_BYTES, &tq, &q_full[qb], h * D, t * QT, b);
             }
         }
-    } else if (warp == 1 || warp == 3) {
+    } else if (warp == 1) {
         if (elect_one()) {
-            // ------------------------------------------------------------ MMA issuer of machine m
-            const int m = warp >> 1;                                    // warp 1 -> 0, warp 3 -> 1
-            constexpr uint32_t idesc_s = make_idesc_f16(QT, SB);       // 128 x 64, both K-major
-            constexpr uint32_t idesc_o = make_idesc_f16(QT, D, 0, 1);  // 128 x 64, B (= V) MN-major
-            const uint32_t q_addr = smem_u32(smem + OFF_Q + m * TILE_BYTES);
+            // ------------------------------------------------------------ S issuer: S_c = Q . K_c^T into S slot c&3
+            constexpr uint32_t idesc_s = make_idesc_f16(QT, SB);  // 128 x 64, both K-major
+            const uint32_t q_addr = smem_u32(smem + OFF_Q);
             const uint32_t k_addr = smem_u32(smem + OFF_K);
-            const uint32_t v_addr = smem_u32(smem + OFF_V);
-            const uint32_t p_addr = smem_u32(smem + OFF_P + m * 2 * TILE_BYTES);
-            const uint32_t tm = tmem_base + m * 256;
-            const int ntiles = (nq - m + 1) / 2;          // query tiles of this machine
-            const int total = ntiles * nsb;               // its stream of sub-blocks
-            if (total > 0) mbar_wait(k_full, 0);
-            auto issue_s = [&](int c) {
-                const int t = c / nsb, sb = c - t * nsb;
-                const uint32_t slot = c & 3;
-                if (sb == 0) mbar_wait(&q_full[m], t & 1);
-                if (c >= 4) mbar_wait(&slot_free[m * 4 + slot], ((c >> 2) - 1) & 1);
+            mbar_wait(k_full, 0);
+            int t = 0, sb = 0;
+            for (int c = 0; c < total; ++c) {  // runs as far ahead as free slots allow
+                const uint32_t slot = c & (NSLOT - 1);
+                if (sb == 0) mbar_wait(&q_full[t & 1], (t >> 1) & 1);
+                if (c >= NSLOT) mbar_wait(&s_free[slot], ((c / NSLOT) - 1) & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k) {
-                    umma_f16_ss(tm + slot * SB, make_sw128_desc(q_addr + k * 32),
+                    umma_f16_ss(tmem_base + TM_S + slot * SB, make_sw128_desc(q_addr + (t & 1) * TILE_BYTES + k * 32),
                                 make_sw128_desc(k_addr + sb * (SB * 128) + k * 32), idesc_s, k != 0);
                 }
-                umma_commit(&s_full[m * 4 + slot]);
-                if (sb == nsb - 1) umma_commit(&q_empty[m]);  // this tile's Q is no longer needed once these retire
-            };
-            if (total > 0) issue_s(0);
-            if (total > 1) issue_s(1);
+                umma_commit(&s_full[slot]);
+                if (++sb == nsb) {
+                    umma_commit(&q_empty[t & 1]);  // this tile's Q is no longer needed once these retire
+                    sb = 0;
+                    ++t;
+                }
+            }
+        }
+    } else if (warp == 3) {
+        if (elect_one()) {
+            // ------------------------------------------------------------ P.V issuer: O_t (+)= P_c . V_c
+            constexpr uint32_t idesc_o = make_idesc_f16(QT, D, 0, 1);  // 128 x 64, B (= V) MN-major
+            const uint32_t v_addr = smem_u32(smem + OFF_V);
+            const uint32_t p_addr = smem_u32(smem + OFF_P);
             if (total > 0) mbar_wait(v_full, 0);
+            int t = 0, sb = 0;
+            uint32_t pb = 0, use = 0;
             for (int c = 0; c < total; ++c) {
-                const int t = c / nsb, sb = c - t * nsb;
-                const uint32_t ps = c & 1, slot = c & 3;
-                ATT_STAMP(2 + m, c, 0);
-                mbar_wait(&p_full[m * 2 + ps], (c >> 1) & 1);
+                ATT_STAMP(4, c, 0);
+                mbar_wait(&p_full[pb], use & 1);
+                if (sb == 0 && t >= 2) mbar_wait(&o_free[t & 1], ((t >> 1) - 1) & 1);  // tile t-2 has been written out
                 tc_fence_after();
-                ATT_STAMP(2 + m, c, 1);
+                ATT_STAMP(4, c, 1);
 #pragma unroll
                 for (int kk = 0; kk < SB / 16; ++kk) {
-                    const uint32_t a = p_addr + ps * TILE_BYTES + kk * 32;
+                    const uint32_t a = p_addr + pb * TILE_BYTES + kk * 32;
                     const uint32_t bv = v_addr + (sb * SB + kk * 16) * 128;  // key row -> 128 B
-                    umma_f16_ss(tm + slot * SB, make_sw128_desc(a), make_sw128_desc(bv), idesc_o, kk != 0);
+                    umma_f16_ss(tmem_base + TM_O + (t & 1) * D, make_sw128_desc(a), make_sw128_desc(bv), idesc_o,
+                                (sb | kk) != 0);
                 }
-                umma_commit(&o_full[m * 4 + slot]);
-                ATT_STAMP(2 + m, c, 2);
-                if (c + 2 < total) issue_s(c + 2);
-                ATT_STAMP(2 + m, c, 3);
+                umma_commit(&pv_done[pb]);  // P buffer pb is free again; O_t is stable until the next P.V
+                ATT_STAMP(4, c, 2);
+                if (++sb == nsb) {
+                    umma_commit(&o_done[t & 1]);
+                    sb = 0;
+                    ++t;
+                }
+                if (++pb == NEXP) {
+                    pb = 0;
+                    ++use;
+                }
             }
         }
-    } else if (warp >= 4) {
-        // ---------------------------------------------------------------- softmax + epilogue warpgroup of machine m
-        const int m = (warp - 4) >> 2;
+    } else if (warp >= 4 && warp < 4 + 4 * NEXP) {
+        // ---------------------------------------------------------------- exp warpgroup w: sub-blocks c = w (mod NEXP)
+        const int w = (warp - 4) >> 2;
+        const int wp = (w + NEXP - 1) % NEXP;  // the warpgroup that handles c - 1
         const int r = (warp & 3) * 32 + lane;  // query row within the tile == TMEM lane
-        const uint32_t tm = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + m * 256;
-        const uint32_t p_base = smem_u32(smem + OFF_P + m * 2 * TILE_BYTES);
+        const uint32_t tm = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        const uint32_t p_row = smem_u32(smem + OFF_P + w * TILE_BYTES) + r * 128;
+        const uint32_t mr_self = smem_u32(smem + OFF_MR) + (w * QT + r) * 4;
+        const uint32_t mr_prev = smem_u32(smem + OFF_MR) + (wp * QT + r) * 4;
+        const uint32_t ls_self = smem_u32(smem + OFF_LS) + (w * QT + r) * 8;
         const uint32_t swz = static_cast<uint32_t>(r & 7);
-        uint32_t c = 0;  // sub-block counter of this machine (continues across its tiles)
         const bool obs = (warp & 3) == 0 && lane == 0;
-        for (int qt = m; qt < nq; qt += 2) {
-            float acc[D];
+        int t = 0, sb = w;
+        while (sb >= nsb) {
+            sb -= nsb;
+            ++t;
+        }
+        float l_w = 0.f, m_ref = 0.f;  // this warpgroup's partial row sum of the tile, relative to m_ref
+        uint32_t use = 0;              // how often this warpgroup's P buffer has been filled
+        if (USE_TOKEN && w == NEXP - 1) named_bar_arrive(BAR_TOKEN, 256);  // warpgroup 0 goes first
+#pragma unroll 1
+        for (int c = w; c < total; c += NEXP, ++use) {
+            const uint32_t slot = c & (NSLOT - 1);
+            if (obs) ATT_STAMP(w, c, 0);
+            mbar_wait(&s_full[slot], (c / NSLOT) & 1);
+            tc_fence_after();
+            if (obs) ATT_STAMP(w, c, 1);
+            const int valid = len - sb * SB;  // keys [0, valid) of this sub-block are real (>= 1)
+            uint32_t v[64];
+            auto load_scores = [&]() {
+                tmem_ld_32x32b_x32(tm + TM_S + slot * SB, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                tmem_ld_32x32b_x32(tm + TM_S + slot * SB + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+                tmem_ld_wait();
+                if (valid < SB) {
 #pragma unroll
-            for (int i = 0; i < D; ++i) acc[i] = 0.f;
-            float m_run = -INFINITY, l_run = 0.f;
-            float mq[2] = {0.f, 0.f}, lq[2] = {0.f, 0.f};  // (m, l) of the two sub-blocks not yet folded
-            // fold sub-block cj (its O is in slot cj&3) into the running state and free the slot
-            // `need_wait`: in the steady state O_cj is already known to be complete (see the s_full note below)
-            auto fold = [&](uint32_t cj, float m_j, float l_j, bool need_wait) {
-                const float m_new = fmaxf(m_run, m_j);
-                const float sc = ex2_approx((m_run - m_new) * kScaleLog2e);  // 0 for the tile's first sub-block
-                const float w = ex2_approx((m_j - m_new) * kScaleLog2e);
-                l_run = fmaf(w, l_j, l_run * sc);
-                m_run = m_new;
-                const uint32_t slot = cj & 3;
-                if (need_wait) {
-                    mbar_wait(&o_full[m * 4 + slot], (cj >> 2) & 1);
-                    tc_fence_after();
+                    for (int e = 0; e < SB; ++e)
+                        if (e >= valid) v[e] = __float_as_uint(-INFINITY);
                 }
+            };
+            load_scores();
+            float mx = -INFINITY;
 #pragma unroll
-                for (int half = 0; half < D / 32; ++half) {
-                    uint32_t o[32];
-                    tmem_ld_32x32b_x32(tm + slot * SB + half * 32, o);
+            for (int e = 0; e < SB; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+            // running reference max: take over the previous sub-block's unless this one exceeds it by > 2^8
+            float m_used = mx, m_prev = mx;
+            if (c > 0) named_bar_sync(BAR_MAX + wp, 256);  // (c-1)'s reference max is in shared memory
+            if (sb != 0) {
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m_prev) : "r"(mr_prev) : "memory");
+                m_used = (mx - m_prev > kRescaleThreshold) ? mx : m_prev;
+            }
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(mr_self), "f"(m_used) : "memory");
+            named_bar_arrive(BAR_MAX + w, 256);
+            if (sb < NEXP) {  // this warpgroup's first sub-block of the tile
+                l_w = 0.f;
+            } else {
+                l_w *= ex2_approx((m_ref - m_used) * kScaleLog2e);
+            }
+            m_ref = m_used;
+            if (obs) ATT_STAMP(w, c, 2);
+            if (sb != 0 && __any_sync(0xffffffffu, m_used != m_prev)) {
+                // rare: rescale this warp's 32 rows of the accumulator by 2^((m_prev - m_used) k) (1 where unchanged).
+                // The scores are dropped and read again afterwards so that this path costs the common one no registers.
+                const int cp = c - 1;
+                mbar_wait(&pv_done[cp % NEXP], (cp / NEXP) & 1);  // O_t is complete up to sub-block c-1
+                tc_fence_after();
+                const float f = ex2_approx((m_prev - m_used) * kScaleLog2e);
+#pragma unroll
+                for (int part = 0; part < D / 32; ++part) {
+                    tmem_ld_32x32b_x32(tm + TM_O + (t & 1) * D + part * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
                     tmem_ld_wait();
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) acc[half * 32 + e] = fmaf(w, __uint_as_float(o[e]), acc[half * 32 + e] * sc);
+                    for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * f);
+                    tmem_st_32x32b_x32(tm + TM_O + (t & 1) * D + part * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
                 }
-                tc_fence_before();
-                mbar_arrive(&slot_free[m * 4 + slot]);
-            };
-#pragma unroll 1
-            for (int sb = 0; sb < nsb; ++sb, ++c) {
-                const uint32_t slot = c & 3, ps = c & 1;
-                if (obs) ATT_STAMP(m, c, 0);
-                // The MMA thread issues PV_{c-2} before S_c and tcgen05.commit arrives only when ALL its earlier MMAs have
-                // retired, so s_full(c) also tells us that O_{c-2} is complete and that P slot c&1 has been consumed:
-                // one barrier wait per sub-block instead of three (each costs ~150-190 cycles even when already complete).
-                mbar_wait(&s_full[m * 4 + slot], (c >> 2) & 1);
-                tc_fence_after();
-                if (obs) ATT_STAMP(m, c, 1);
-                const int valid = len - sb * SB;  // keys [0, valid) of this sub-block are real (>= 1)
-                uint32_t v[64];
-                tmem_ld_32x32b_x32(tm + slot * SB, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-                tmem_ld_32x32b_x32(tm + slot * SB + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-                tmem_ld_wait();
-                float mx = -INFINITY;
-                if (valid >= SB) {
-#pragma unroll
-                    for (int e = 0; e < SB; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
-                } else {
-#pragma unroll
-                    for (int e = 0; e < SB; ++e) {
-                        if (e >= valid) v[e] = __float_as_uint(-INFINITY);
-                        mx = fmaxf(mx, __uint_as_float(v[e]));
-                    }
-                }
-                const float neg_ms = -mx * kScaleLog2e;
-                if (obs) ATT_STAMP(m, c, 3);
-                float ls0 = 0.f, ls1 = 0.f;
-                const uint32_t row_ptr = p_base + ps * TILE_BYTES + r * 128;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(v[q * 8 + 2 * e]), kScaleLog2e, neg_ms));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(v[q * 8 + 2 * e + 1]), kScaleLog2e, neg_ms));
-                        ls0 += p0;
-                        ls1 += p1;
-                        pk[e] = pack_half2(p0, p1);
-                    }
-                    // keys 8q .. 8q+7 of row r -> 16-byte chunk q ^ (r & 7) of the row's 128 bytes
-                    sts128(row_ptr + ((static_cast<uint32_t>(q) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
-                }
-                tc_fence_before();         // our TMEM reads of S_c precede the MMA that overwrites it with O_c
-                fence_proxy_async_smem();  // P_c visible to the tensor core's async-proxy reads
-                mbar_arrive(&p_full[m * 2 + ps]);
-                if (obs) ATT_STAMP(m, c, 4);
-                if (sb >= 2) fold(c - 2, mq[sb & 1], lq[sb & 1], false);
-                if (obs) ATT_STAMP(m, c, 5);
-                mq[sb & 1] = mx;
-                lq[sb & 1] = ls0 + ls1;
+                tmem_st_wait();
+                load_scores();
             }
-            // drain the (up to) two sub-blocks still in flight
-            if (nsb >= 2) fold(c - 2, mq[nsb & 1], lq[nsb & 1], true);
-            fold(c - 1, mq[(nsb - 1) & 1], lq[(nsb - 1) & 1], true);
-            if (obs) ATT_STAMP(m, c - 1, 6);
-            const float inv_l = 1.0f / l_run;
-            const int q_row = qt * QT + r;
-            if (q_row < S) {
-                uint4* dst = reinterpret_cast<uint4*>(ctx + (static_cast<size_t>(b) * S + q_row) * HIDDEN + h * D);
+            tc_fence_before();
+            mbar_arrive(&s_free[slot]);  // the scores live in registers from here on
+            const float neg_ms = -m_used * kScaleLog2e;
+            if (use > 0) mbar_wait(&pv_done[w], (use - 1) & 1);  // the previous P of this buffer has been consumed
+            if (USE_TOKEN) named_bar_sync(BAR_TOKEN + w, 256);
+            if (obs) ATT_STAMP(w, c, 3);
+            float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
-                for (int i = 0; i < D / 8; ++i) {
-                    dst[i] = make_uint4(pack_half2(acc[8 * i] * inv_l, acc[8 * i + 1] * inv_l),
-                                        pack_half2(acc[8 * i + 2] * inv_l, acc[8 * i + 3] * inv_l),
-                                        pack_half2(acc[8 * i + 4] * inv_l, acc[8 * i + 5] * inv_l),
-                                        pack_half2(acc[8 * i + 6] * inv_l, acc[8 * i + 7] * inv_l));
+            for (int q = 0; q < 8; ++q) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(v[q * 8 + 2 * e]), kScaleLog2e, neg_ms));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(v[q * 8 + 2 * e + 1]), kScaleLog2e, neg_ms));
+                    ls0 += p0;
+                    ls1 += p1;
+                    pk[e] = pack_half2(p0, p1);
                 }
+                // keys 8q .. 8q+7 of row r -> 16-byte chunk q ^ (r & 7) of the row's 128 bytes
+                sts128(p_row + ((static_cast<uint32_t>(q) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
+            }
+            if (USE_TOKEN) named_bar_arrive(BAR_TOKEN + (w + 1 == NEXP ? 0 : w + 1), 256);  // MUFU to the next warpgroup
+            l_w += ls0 + ls1;
+            if (sb + NEXP >= nsb)  // this warpgroup's last sub-block of the tile
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(ls_self + t * (NEXP * QT * 8)), "f"(m_ref), "f"(l_w) : "memory");
+            tc_fence_before();         // our TMEM accesses precede the MMA that accumulates into O_t
+            fence_proxy_async_smem();  // P_c visible to the tensor core's async-proxy reads
+            mbar_arrive(&p_full[w]);   // (release: also publishes (m, l) to the epilogue via the o_done chain)
+            if (obs) ATT_STAMP(w, c, 4);
+            sb += NEXP;
+            while (sb >= nsb) {
+                sb -= nsb;
+                ++t;
             }
         }
+    } else if (warp >= 4 + 4 * NEXP) {
+        // ---------------------------------------------------------------- epilogue warpgroup: ctx = O_t / l
+        const int r = (warp & 3) * 32 + lane;
+        const uint32_t tm = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+        const uint32_t ls_base = smem_u32(smem + OFF_LS) + r * 8;
+        const uint32_t o_row = smem_u32(smem + OFF_O) + r * 128;
+        const uint32_t swz = static_cast<uint32_t>(r & 7);
+        const bool obs = (warp & 3) == 0 && lane == 0;
+#pragma unroll 1
+        for (int t = 0; t < nq; ++t) {
+            if (obs) ATT_STAMP(3, t, 0);
+            mbar_wait(&o_done[t & 1], (t >> 1) & 1);
+            tc_fence_after();
+            if (obs) ATT_STAMP(3, t, 1);
+            const int c_first = t * nsb;
+            const int w_last = (c_first + nsb - 1) % NEXP;
+            float m_fin, l_fin;
+            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_fin), "=f"(l_fin) : "r"(ls_base + (t * NEXP + w_last) * (QT * 8)) : "memory");
+#pragma unroll
+            for (int w = 0; w < NEXP; ++w) {
+                const int first_sb = (w - c_first % NEXP + NEXP) % NEXP;  // warpgroup w's first sub-block in this tile
+                if (w != w_last && first_sb < nsb) {
+                    float m_w, l_w;
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_w), "=f"(l_w) : "r"(ls_base + (t * NEXP + w) * (QT * 8)) : "memory");
+                    l_fin = fmaf(l_w, ex2_approx((m_w - m_fin) * kScaleLog2e), l_fin);
+                }
+            }
+            const float inv_l = 1.0f / l_fin;
+            // the previous tile's TMA store has finished reading the staging tile
+            if (warp == 4 + 4 * NEXP && lane == 0) tma_store_wait_read<0>();
+            named_bar_sync(BAR_EPI, 128);
+#pragma unroll
+            for (int part = 0; part < D / 32; ++part) {
+                uint32_t o[32];
+                tmem_ld_32x32b_x32(tm + TM_O + (t & 1) * D + part * 32, o);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    // output dims 8j .. 8j+7 of row r -> 16-byte chunk j ^ (r & 7) of the row's 128 bytes
+                    const uint32_t j = part * 4 + i;
+                    sts128(o_row + ((j ^ swz) << 4),
+                           pack_half2(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l),
+                           pack_half2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l),
+                           pack_half2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l),
+                           pack_half2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&o_free[t & 1]);
+            fence_proxy_async_smem();
+            named_bar_sync(BAR_EPI, 128);
+            if (warp == 4 + 4 * NEXP && lane == 0) {  // rows past S are clipped by the tensor map
+                tma_store_3d(&tctx, smem + OFF_O, h * D, t * QT, b);
+                tma_store_commit();
+            }
+            if (obs) ATT_STAMP(3, t, 2);
+        }
+        if (warp == 4 + 4 * NEXP && lane == 0) tma_store_wait_read<0>();  // shared memory must outlive the last store's reads
     }
 
     tc_fence_before();
@@ -293,10 +393,10 @@ cudaError_t attention_init_device() {
     return cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES);
 }
 
-cudaError_t launch_attention(const CUtensorMap& tq, const int32_t* lens, __half* ctx, int B, int S,
+cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tctx, const int32_t* lens, int B, int S,
                              cudaStream_t stream, unsigned long long* dbg) {
     if (S < 1 || S > attn::MAX_KB * attn::KB || B < 1) return cudaErrorInvalidValue;
-    attn::attention_kernel<<<B * HEADS, attn::NUM_THREADS, attn::SMEM_BYTES, stream>>>(tq, lens, ctx, S, dbg);
+    attn::attention_kernel<<<B * HEADS, attn::NUM_THREADS, attn::SMEM_BYTES, stream>>>(tq, tctx, lens, S, dbg);
     return cudaGetLastError();
 }
 

@@ -110,10 +110,11 @@ int make_map_2d_f32(CUtensorMap* m, const void* base, uint64_t rows, uint64_t co
     return 0;
 }
 
-// fp16 qkv [B, S, 2304] -> box {64, 128, 1}, 128B swizzle (rows past S are zero-filled)
-int make_map_qkv(CUtensorMap* m, const void* base, uint64_t B, uint64_t S) {
-    cuuint64_t dims[3] = {QKV_DIM, S, B};
-    cuuint64_t strides[2] = {QKV_DIM * 2, S * QKV_DIM * 2};
+// fp16 [B, S, width] (qkv: width 2304, ctx: width 768) -> box {64, 128, 1}, 128B swizzle (rows past S are zero-filled
+// on load and clipped on store)
+int make_map_qkv(CUtensorMap* m, const void* base, uint64_t B, uint64_t S, uint64_t width = QKV_DIM) {
+    cuuint64_t dims[3] = {width, S, B};
+    cuuint64_t strides[2] = {width * 2, S * width * 2};
     cuuint32_t box[3] = {64, 128, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
@@ -160,7 +161,7 @@ struct Dev {
     CUtensorMap m_x16, m_ctx, m_ffn;      // fp16 [rows,*] box {64,128}: GEMM A operands (m_ffn is also FFN1's output map)
     CUtensorMap m_qkv2d;                  // fp16 [rows,2304] box {64,128}: QKV GEMM output
     CUtensorMap m_y32;                    // fp32 [rows,768] box {32,128}: the fp32 epilogues update y32 in place
-    std::unordered_map<int, CUtensorMap> m_qkv_by_S;
+    std::unordered_map<int, std::pair<CUtensorMap, CUtensorMap>> m_qkv_by_S;  // (qkv, ctx) 3D maps per padded length
     // wave input slots (written by the root's scatter kernel, possibly over NVLink)
     int32_t* ids_in[NSLOT] = {nullptr, nullptr, nullptr};
     int32_t* lens_in[NSLOT] = {nullptr, nullptr, nullptr};
@@ -233,16 +234,19 @@ struct Prof {
     std::vector<cudaEvent_t> evs;
 };
 
-int get_qkv_map(Dev& d, int S, const CUtensorMap** out) {
+int get_qkv_map(Dev& d, int S, const CUtensorMap** out, const CUtensorMap** out_ctx) {
     auto it = d.m_qkv_by_S.find(S);
     if (it == d.m_qkv_by_S.end()) {
-        CUtensorMap m;
+        CUtensorMap m, mc;
         const uint64_t B = static_cast<uint64_t>(g_rt->cap_rows) / S;
         int rc = make_map_qkv(&m, d.qkv, B, S);
         if (rc) return rc;
-        it = d.m_qkv_by_S.emplace(S, m).first;
+        rc = make_map_qkv(&mc, d.ctx, B, S, HIDDEN);
+        if (rc) return rc;
+        it = d.m_qkv_by_S.emplace(S, std::make_pair(m, mc)).first;
     }
-    *out = &it->second;
+    *out = &it->second.first;
+    *out_ctx = &it->second.second;
     return 0;
 }
 
@@ -256,8 +260,8 @@ int forward_enqueue(Dev& d, const Model& m, int dev_index, const int32_t* ids, c
     const bool full = n_layers < 0;
     const int M = B * S;
     if (M > g_rt->cap_rows) return fail(B200RT_E_INVALID, "batch of %d x %d tokens exceeds wave capacity %d rows", B, S, g_rt->cap_rows);
-    const CUtensorMap* mq = nullptr;
-    if (int rc = get_qkv_map(d, S, &mq)) return rc;
+    const CUtensorMap *mq = nullptr, *mc = nullptr;
+    if (int rc = get_qkv_map(d, S, &mq, &mc)) return rc;
     uint64_t nl = 0;
     auto mark = [&](const char* name) {
         if (prof) {
@@ -277,7 +281,7 @@ int forward_enqueue(Dev& d, const Model& m, int dev_index, const int32_t* ids, c
         const LayerW& lw = w.layers[l];
         CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_x16, lw.m_qkv, d.m_qkv2d, nullptr, lw.qkv_b, M, QKV_DIM, HIDDEN, d.sm_count, stream));
         ++nl; mark("gemm_qkv");
-        CUDA_TRY(launch_attention(*mq, lens, d.ctx, B, S, stream));
+        CUDA_TRY(launch_attention(*mq, *mc, lens, B, S, stream));
         ++nl; mark("attention");
         CUDA_TRY(launch_gemm(EPI_BIAS_RES_F32, d.m_ctx, lw.m_ao, d.m_y32, &prev, lw.ao_b, M, HIDDEN, HIDDEN, d.sm_count, stream));
         ++nl; mark("gemm_attn_out");
@@ -346,8 +350,8 @@ int forward(Dev& d, const Model& m, int dev_index, const int32_t* ids, const int
     auto it = cache.find(key);
     if (it == cache.end()) {
         if (cache.size() >= GRAPH_CACHE_MAX) return forward_enqueue(d, m, dev_index, ids, lens, B, S, out, stream, -1, nullptr, launches);
-        const CUtensorMap* mq = nullptr;
-        if (int rc = get_qkv_map(d, S, &mq)) return rc;  // host-side map creation happens outside the capture
+        const CUtensorMap *mq = nullptr, *mc = nullptr;
+        if (int rc = get_qkv_map(d, S, &mq, &mc)) return rc;  // host-side map creation happens outside the capture
         uint64_t nl = 0;
         CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
         const int rc = forward_enqueue(d, m, dev_index, ids, lens, B, S, out, stream, -1, nullptr, &nl);
@@ -1064,15 +1068,16 @@ int b200rt_debug_attention(const uint16_t* qkv, const int32_t* lens, uint16_t* c
     CUDA_TRY(cudaMemset(dc, 0xFF, M * HIDDEN * 2));
     CUDA_TRY(cudaMemcpy(dq, qkv, M * QKV_DIM * 2, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(dl_, lens, static_cast<size_t>(B) * 4, cudaMemcpyHostToDevice));
-    CUtensorMap tq;
+    CUtensorMap tq, tc;
     if (int rc = make_map_qkv(&tq, dq, B, S)) return rc;
+    if (int rc = make_map_qkv(&tc, dc, B, S, HIDDEN)) return rc;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     if (iters < 1) iters = 1;
-    CUDA_TRY(launch_attention(tq, dl_, dc, B, S, d.compute));
+    CUDA_TRY(launch_attention(tq, tc, dl_, B, S, d.compute));
     CUDA_TRY(cudaEventRecord(e0, d.compute));
-    for (int i = 0; i < iters; ++i) CUDA_TRY(launch_attention(tq, dl_, dc, B, S, d.compute));
+    for (int i = 0; i < iters; ++i) CUDA_TRY(launch_attention(tq, tc, dl_, B, S, d.compute));
     CUDA_TRY(cudaEventRecord(e1, d.compute));
     CUDA_TRY(cudaStreamSynchronize(d.compute));
     float ms = 0;
@@ -1081,17 +1086,17 @@ int b200rt_debug_attention(const uint16_t* qkv, const int32_t* lens, uint16_t* c
     CUDA_TRY(cudaMemcpy(ctx, dc, M * HIDDEN * 2, cudaMemcpyDeviceToHost));
     if (const char* path = getenv("B200RT_ATTN_STAMPS")) {  // diagnostics: per-phase clock stamps of CTA 0 -> text file
         unsigned long long* dstamp = nullptr;
-        std::vector<unsigned long long> hs(4 * 32 * 8, 0);
+        std::vector<unsigned long long> hs(5 * 32 * 8, 0);
         CUDA_TRY(cudaMalloc(&dstamp, hs.size() * 8));
         CUDA_TRY(cudaMemset(dstamp, 0, hs.size() * 8));
-        CUDA_TRY(launch_attention(tq, dl_, dc, B, S, d.compute, dstamp));
+        CUDA_TRY(launch_attention(tq, tc, dl_, B, S, d.compute, dstamp));
         CUDA_TRY(cudaStreamSynchronize(d.compute));
         CUDA_TRY(cudaMemcpy(hs.data(), dstamp, hs.size() * 8, cudaMemcpyDeviceToHost));
         unsigned long long t0 = ~0ull;
         for (auto v : hs) if (v && v < t0) t0 = v;
         if (FILE* f = fopen(path, "w")) {
-            const char* names[4] = {"softmax_m0", "softmax_m1", "mma_m0", "mma_m1"};
-            for (int o = 0; o < 4; ++o)
+            const char* names[5] = {"exp_wg0", "exp_wg1", "exp_wg2", "fold", "mma"};
+            for (int o = 0; o < 5; ++o)
                 for (int c = 0; c < 32; ++c) {
                     bool any = false;
                     for (int sl = 0; sl < 8; ++sl) any |= hs[(o * 32 + c) * 8 + sl] != 0;

@@ -38,9 +38,10 @@ cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
                         const float* bias, int M, int N, int K, int sm_count, cudaStream_t stream);
 
 // Multi-head self-attention over a padded batch: qkv fp16 [B, S, 2304] (Q | K | V, head-major within each),
-// lens[B] valid keys per item, ctx fp16 [B*S, 768].  tq: 3D map over qkv {2304, S, B}, box {64,128,1}, 128B swizzle.
-// dbg: optional device buffer of 4*32*8 clock stamps written by CTA 0 (diagnostics; NULL in the product path)
-cudaError_t launch_attention(const CUtensorMap& tq, const int32_t* lens, __half* ctx, int B, int S,
+// lens[B] valid keys per item, ctx fp16 [B*S, 768].  tq: 3D map over qkv {2304, S, B}, tctx: 3D map over ctx {768, S, B};
+// both box {64,128,1}, 128B swizzle.
+// dbg: optional device buffer of 5*32*8 clock stamps written by CTA 0 (diagnostics; NULL in the product path)
+cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tctx, const int32_t* lens, int B, int S,
                              cudaStream_t stream, unsigned long long* dbg = nullptr);
 
 // word + position + token_type(0) embedding gather -> y32 (fp32 pre-LN sum = residual stream), LayerNorm ->
