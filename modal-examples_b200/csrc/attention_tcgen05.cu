@@ -25,6 +25,8 @@
 //
 // Restates BertSelfAttention.forward (HF modeling_bert.py:143-207) for the TEI /embed path the
 // reference calls at 06_gpu_and_ml/embeddings/text_embeddings_inference.py:100.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -38,30 +40,43 @@ constexpr int D = HEAD_DIM;  // 64
 constexpr int MAX_KB = 4;    // S <= 512
 constexpr int MAX_NQ = 4;
 constexpr int NSLOT = 4;     // TMEM S slots of 64 columns
-constexpr int NEXP = 2;      // exp warpgroups == P buffers
-constexpr bool USE_TOKEN = true;
-constexpr uint32_t TM_O = 0;            // 2 x 64 columns
-constexpr uint32_t TM_S = 2 * D;        // NSLOT x 64 columns
+constexpr int NEXP = 2;      // exp warpgroups == P buffers == accumulators per tile
+constexpr uint32_t TM_O = 0;                // accumulators: (tile parity, warpgroup) -> 2 x NEXP x 64 columns
+constexpr uint32_t TM_S = 2 * NEXP * D;     // S ring: NSLOT x 64 columns
 constexpr int TILE_BYTES = 128 * D * 2;  // 16 KB: 128 rows x 128 B
 constexpr int OFF_Q = 0;                            // 2 x 16 KB (double buffered across tiles)
 constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;       // 4 x 16 KB
 constexpr int OFF_V = OFF_K + MAX_KB * TILE_BYTES;  // 4 x 16 KB
-constexpr int OFF_P = OFF_V + MAX_KB * TILE_BYTES;  // NEXP x 16 KB
-constexpr int OFF_O = OFF_P + NEXP * TILE_BYTES;    // 16 KB: the epilogue's staging tile for the TMA store
-constexpr int OFF_MR = OFF_O + TILE_BYTES;            // float [NEXP][128]: reference max after warpgroup w's latest sub-block
-constexpr int OFF_LS = OFF_MR + NEXP * QT * 4;      // float2 [MAX_NQ][NEXP][128]: (reference max, partial sum) per tile
+constexpr int OFF_O = OFF_V + MAX_KB * TILE_BYTES;  // 16 KB: the epilogue's staging tile for the TMA store
+constexpr int OFF_LS = OFF_O + TILE_BYTES;          // float2 [MAX_NQ][NEXP][128]: (reference max, row sum) per tile and warpgroup
 constexpr int OFF_BAR = OFF_LS + MAX_NQ * NEXP * QT * 8;
-constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
+constexpr int OFF_P = (OFF_BAR + 512 + 1023) / 1024 * 1024;  // NEXP x 16 KB, 1024-aligned for the 128B swizzle
+static_assert(OFF_P % 1024 == 0 && OFF_O % 1024 == 0 && OFF_V % 1024 == 0, "swizzled tiles must be 1024-byte aligned");
+constexpr int SMEM_BYTES = OFF_P + NEXP * TILE_BYTES + 1024;
 constexpr int NUM_THREADS = 128 + NEXP * 128 + 128;
-constexpr int BAR_TOKEN = 1;         // named barriers 1 .. NEXP: MUFU token
-constexpr int BAR_MAX = 1 + NEXP;    // named barriers 1+NEXP .. 2 NEXP: running-max hand-off
-constexpr int BAR_EPI = 1 + 2 * NEXP;  // the epilogue warpgroup's own barrier
+constexpr int BAR_TOKEN = 1;             // named barriers 1 .. NEXP: MUFU token
+constexpr int BAR_EPI = 1 + NEXP;        // the epilogue warpgroup's own barrier
 
 // softmax_scale * log2(e) with softmax_scale = 1/sqrt(64)
 constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;
 // the reference max follows the true max only when it is exceeded by more than this (raw score units): P <= 2^8
 constexpr float kRescaleThreshold = 8.0f / kScaleLog2e;
 
+// 2^x for x <= ~8 on the FMA pipe: round-to-nearest split x = i + f, |f| <= 0.5, degree-3 minimax for 2^f (7.5e-5 relative,
+// well inside fp16's 4.9e-4), exponent added as an integer.  x is clamped at -126 (also maps a masked -inf to ~0).
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.0f);
+    const float t = x + 12582912.0f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
+    const float f = x - (t - 12582912.0f);
+    float p = fmaf(0.05517163872718811f, f, 0.2426111251115799f);
+    p = fmaf(p, f, 0.6932609677314758f);
+    p = fmaf(p, f, 0.9999280571937561f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// USE_TOKEN: the exp phases of the warpgroups take turns on the MUFU.  POLY: of every 8 scores, this many take ex2_poly
+// instead of MUFU.EX2 (a single warp's MUFU stream sustains one EX2 per ~11 cycles; the FMA pipe has slots to spare).
+template <bool USE_TOKEN, int POLY>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tctx,
                  const int32_t* __restrict__ lens, int S, unsigned long long* __restrict__ dbg) {
@@ -84,7 +99,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
     uint64_t* s_free = bars + 14;      // [NSLOT]  S_c is in the exp warpgroup's registers
     uint64_t* p_full = bars + 18;      // [NEXP]  P buffer w written
     uint64_t* pv_done = bars + 22;     // [NEXP]  the P.V reading P buffer w has retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
     const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
     const int lane = lane_id();
@@ -174,7 +189,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
         }
     } else if (warp == 3) {
         if (elect_one()) {
-            // ------------------------------------------------------------ P.V issuer: O_t (+)= P_c . V_c
+            // ------------------------------------------------------------ P.V issuer: O_{t,w} (+)= P_c . V_c, w = c mod NEXP
             constexpr uint32_t idesc_o = make_idesc_f16(QT, D, 0, 1);  // 128 x 64, B (= V) MN-major
             const uint32_t v_addr = smem_u32(smem + OFF_V);
             const uint32_t p_addr = smem_u32(smem + OFF_P);
@@ -191,10 +206,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 for (int kk = 0; kk < SB / 16; ++kk) {
                     const uint32_t a = p_addr + pb * TILE_BYTES + kk * 32;
                     const uint32_t bv = v_addr + (sb * SB + kk * 16) * 128;  // key row -> 128 B
-                    umma_f16_ss(tmem_base + TM_O + (t & 1) * D, make_sw128_desc(a), make_sw128_desc(bv), idesc_o,
-                                (sb | kk) != 0);
+                    // warpgroup pb's accumulator of tile t; its first sub-block of the tile (sb < NEXP) overwrites
+                    umma_f16_ss(tmem_base + TM_O + ((t & 1) * NEXP + pb) * D, make_sw128_desc(a), make_sw128_desc(bv),
+                                idesc_o, (sb >= NEXP) || kk != 0);
                 }
-                umma_commit(&pv_done[pb]);  // P buffer pb is free again; O_t is stable until the next P.V
+                umma_commit(&pv_done[pb]);  // P buffer pb is free again; O_{t,pb} is stable until warpgroup pb's next P.V
                 ATT_STAMP(4, c, 2);
                 if (++sb == nsb) {
                     umma_commit(&o_done[t & 1]);
@@ -210,12 +226,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
     } else if (warp >= 4 && warp < 4 + 4 * NEXP) {
         // ---------------------------------------------------------------- exp warpgroup w: sub-blocks c = w (mod NEXP)
         const int w = (warp - 4) >> 2;
-        const int wp = (w + NEXP - 1) % NEXP;  // the warpgroup that handles c - 1
         const int r = (warp & 3) * 32 + lane;  // query row within the tile == TMEM lane
         const uint32_t tm = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
         const uint32_t p_row = smem_u32(smem + OFF_P + w * TILE_BYTES) + r * 128;
-        const uint32_t mr_self = smem_u32(smem + OFF_MR) + (w * QT + r) * 4;
-        const uint32_t mr_prev = smem_u32(smem + OFF_MR) + (wp * QT + r) * 4;
         const uint32_t ls_self = smem_u32(smem + OFF_LS) + (w * QT + r) * 8;
         const uint32_t swz = static_cast<uint32_t>(r & 7);
         const bool obs = (warp & 3) == 0 && lane == 0;
@@ -224,7 +237,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             sb -= nsb;
             ++t;
         }
-        float l_w = 0.f, m_ref = 0.f;  // this warpgroup's partial row sum of the tile, relative to m_ref
+        float l_w = 0.f, m_ref = 0.f;  // this warpgroup's row sum of the tile, and the reference max it is relative to
         uint32_t use = 0;              // how often this warpgroup's P buffer has been filled
         if (USE_TOKEN && w == NEXP - 1) named_bar_arrive(BAR_TOKEN, 256);  // warpgroup 0 goes first
 #pragma unroll 1
@@ -250,43 +263,34 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             float mx = -INFINITY;
 #pragma unroll
             for (int e = 0; e < SB; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
-            // running reference max: take over the previous sub-block's unless this one exceeds it by > 2^8
-            float m_used = mx, m_prev = mx;
-            if (c > 0) named_bar_sync(BAR_MAX + wp, 256);  // (c-1)'s reference max is in shared memory
-            if (sb != 0) {
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m_prev) : "r"(mr_prev) : "memory");
-                m_used = (mx - m_prev > kRescaleThreshold) ? mx : m_prev;
-            }
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(mr_self), "f"(m_used) : "memory");
-            named_bar_arrive(BAR_MAX + w, 256);
-            if (sb < NEXP) {  // this warpgroup's first sub-block of the tile
-                l_w = 0.f;
-            } else {
-                l_w *= ex2_approx((m_ref - m_used) * kScaleLog2e);
-            }
-            m_ref = m_used;
+            // reference max of this warpgroup's accumulator: moves only when exceeded by more than 2^8 in the exp2 domain
+            const bool first = sb < NEXP;  // this warpgroup's first sub-block of the tile
+            const float m_prev = m_ref;
+            if (first || mx - m_ref > kRescaleThreshold) m_ref = mx;
+            if (first) l_w = 0.f;
             if (obs) ATT_STAMP(w, c, 2);
-            if (sb != 0 && __any_sync(0xffffffffu, m_used != m_prev)) {
-                // rare: rescale this warp's 32 rows of the accumulator by 2^((m_prev - m_used) k) (1 where unchanged).
+            if (!first && __any_sync(0xffffffffu, m_ref != m_prev)) {
+                // rare: rescale this warp's 32 rows of the accumulator by 2^((m_prev - m_ref) k) (1 where unchanged).
                 // The scores are dropped and read again afterwards so that this path costs the common one no registers.
-                const int cp = c - 1;
-                mbar_wait(&pv_done[cp % NEXP], (cp / NEXP) & 1);  // O_t is complete up to sub-block c-1
+                mbar_wait(&pv_done[w], (use - 1) & 1);  // our previous P.V has retired: the accumulator is stable
                 tc_fence_after();
-                const float f = ex2_approx((m_prev - m_used) * kScaleLog2e);
+                const float f = ex2_approx((m_prev - m_ref) * kScaleLog2e);
+                l_w *= f;
+                const uint32_t o_addr = tm + TM_O + ((t & 1) * NEXP + w) * D;
 #pragma unroll
                 for (int part = 0; part < D / 32; ++part) {
-                    tmem_ld_32x32b_x32(tm + TM_O + (t & 1) * D + part * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                    tmem_ld_32x32b_x32(o_addr + part * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
                     tmem_ld_wait();
 #pragma unroll
                     for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * f);
-                    tmem_st_32x32b_x32(tm + TM_O + (t & 1) * D + part * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+                    tmem_st_32x32b_x32(o_addr + part * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
                 }
                 tmem_st_wait();
                 load_scores();
             }
             tc_fence_before();
             mbar_arrive(&s_free[slot]);  // the scores live in registers from here on
-            const float neg_ms = -m_used * kScaleLog2e;
+            const float neg_ms = -m_ref * kScaleLog2e;
             if (use > 0) mbar_wait(&pv_done[w], (use - 1) & 1);  // the previous P of this buffer has been consumed
             if (USE_TOKEN) named_bar_sync(BAR_TOKEN + w, 256);
             if (obs) ATT_STAMP(w, c, 3);
@@ -296,8 +300,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 uint32_t pk[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(v[q * 8 + 2 * e]), kScaleLog2e, neg_ms));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(v[q * 8 + 2 * e + 1]), kScaleLog2e, neg_ms));
+                    const float x0 = fmaf(__uint_as_float(v[q * 8 + 2 * e]), kScaleLog2e, neg_ms);
+                    const float x1 = fmaf(__uint_as_float(v[q * 8 + 2 * e + 1]), kScaleLog2e, neg_ms);
+                    // POLY of each 8 go to the FMA pipe, spread over the 8 so that they fill the MUFU's shadow
+                    const float p0 = (POLY >= 3 && e == 1) || (POLY >= 4 && e == 3) ? ex2_poly(x0) : ex2_approx(x0);
+                    const float p1 = (POLY >= 1 && e == 3) || (POLY >= 2 && e == 1) ? ex2_poly(x1) : ex2_approx(x1);
                     ls0 += p0;
                     ls1 += p1;
                     pk[e] = pack_half2(p0, p1);
@@ -333,37 +340,55 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             mbar_wait(&o_done[t & 1], (t >> 1) & 1);
             tc_fence_after();
             if (obs) ATT_STAMP(3, t, 1);
+            // combine the warpgroups' accumulators: O = sum_w 2^((m_w - m) k) O_w, l likewise, m = max_w m_w
             const int c_first = t * nsb;
-            const int w_last = (c_first + nsb - 1) % NEXP;
-            float m_fin, l_fin;
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_fin), "=f"(l_fin) : "r"(ls_base + (t * NEXP + w_last) * (QT * 8)) : "memory");
+            float m_w[NEXP], l_w[NEXP], f_w[NEXP];
+            bool part_w[NEXP];
+            float m_fin = -INFINITY;
 #pragma unroll
             for (int w = 0; w < NEXP; ++w) {
-                const int first_sb = (w - c_first % NEXP + NEXP) % NEXP;  // warpgroup w's first sub-block in this tile
-                if (w != w_last && first_sb < nsb) {
-                    float m_w, l_w;
-                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_w), "=f"(l_w) : "r"(ls_base + (t * NEXP + w) * (QT * 8)) : "memory");
-                    l_fin = fmaf(l_w, ex2_approx((m_w - m_fin) * kScaleLog2e), l_fin);
+                part_w[w] = (w - c_first % NEXP + NEXP) % NEXP < nsb;  // warpgroup w had a sub-block in this tile
+                m_w[w] = -INFINITY;
+                l_w[w] = 0.f;
+                if (part_w[w]) {
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_w[w]), "=f"(l_w[w]) : "r"(ls_base + (t * NEXP + w) * (QT * 8)) : "memory");
+                    m_fin = fmaxf(m_fin, m_w[w]);
                 }
             }
+            float l_fin = 0.f;
+#pragma unroll
+            for (int w = 0; w < NEXP; ++w) {
+                f_w[w] = part_w[w] ? ex2_approx((m_w[w] - m_fin) * kScaleLog2e) : 0.f;
+                l_fin = fmaf(l_w[w], f_w[w], l_fin);
+            }
             const float inv_l = 1.0f / l_fin;
+#pragma unroll
+            for (int w = 0; w < NEXP; ++w) f_w[w] *= inv_l;
             // the previous tile's TMA store has finished reading the staging tile
             if (warp == 4 + 4 * NEXP && lane == 0) tma_store_wait_read<0>();
             named_bar_sync(BAR_EPI, 128);
 #pragma unroll
             for (int part = 0; part < D / 32; ++part) {
-                uint32_t o[32];
-                tmem_ld_32x32b_x32(tm + TM_O + (t & 1) * D + part * 32, o);
-                tmem_ld_wait();
+                float acc[32];
+#pragma unroll
+                for (int e = 0; e < 32; ++e) acc[e] = 0.f;
+#pragma unroll
+                for (int w = 0; w < NEXP; ++w) {
+                    if (part_w[w]) {  // (uniform)
+                        uint32_t o[32];
+                        tmem_ld_32x32b_x32(tm + TM_O + ((t & 1) * NEXP + w) * D + part * 32, o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) acc[e] = fmaf(f_w[w], __uint_as_float(o[e]), acc[e]);
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     // output dims 8j .. 8j+7 of row r -> 16-byte chunk j ^ (r & 7) of the row's 128 bytes
                     const uint32_t j = part * 4 + i;
-                    sts128(o_row + ((j ^ swz) << 4),
-                           pack_half2(__uint_as_float(o[8 * i]) * inv_l, __uint_as_float(o[8 * i + 1]) * inv_l),
-                           pack_half2(__uint_as_float(o[8 * i + 2]) * inv_l, __uint_as_float(o[8 * i + 3]) * inv_l),
-                           pack_half2(__uint_as_float(o[8 * i + 4]) * inv_l, __uint_as_float(o[8 * i + 5]) * inv_l),
-                           pack_half2(__uint_as_float(o[8 * i + 6]) * inv_l, __uint_as_float(o[8 * i + 7]) * inv_l));
+                    sts128(o_row + ((j ^ swz) << 4), pack_half2(acc[8 * i], acc[8 * i + 1]),
+                           pack_half2(acc[8 * i + 2], acc[8 * i + 3]), pack_half2(acc[8 * i + 4], acc[8 * i + 5]),
+                           pack_half2(acc[8 * i + 6], acc[8 * i + 7]));
                 }
             }
             tc_fence_before();
@@ -389,14 +414,46 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
 
 }  // namespace attn
 
+namespace {
+// diagnostics: B200RT_ATTN_VARIANT = "<t|n><0..4>": exp phases take turns on the MUFU (t) or overlap freely (n), and how many
+// of every 8 exponentials run as a polynomial on the FMA pipe.  The product default is the fastest measured combination.
+constexpr int kDefaultVariant = 0 * 5 + 0;  // token, POLY 0
+int attention_variant() {
+    static const int v = [] {
+        const char* e = getenv("B200RT_ATTN_VARIANT");
+        if (!e || (e[0] != 't' && e[0] != 'n') || e[1] < '0' || e[1] > '4') return kDefaultVariant;
+        return (e[0] == 'n' ? 5 : 0) + (e[1] - '0');
+    }();
+    return v;
+}
+template <bool TOKEN, int POLY>
+cudaError_t set_smem() {
+    return cudaFuncSetAttribute(attn::attention_kernel<TOKEN, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES);
+}
+template <bool TOKEN, int POLY>
+void launch(const CUtensorMap& tq, const CUtensorMap& tctx, const int32_t* lens, int B, int S, cudaStream_t stream,
+            unsigned long long* dbg) {
+    attn::attention_kernel<TOKEN, POLY><<<B * HEADS, attn::NUM_THREADS, attn::SMEM_BYTES, stream>>>(tq, tctx, lens, S, dbg);
+}
+}  // namespace
+
 cudaError_t attention_init_device() {
-    return cudaFuncSetAttribute(attn::attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES);
+    cudaError_t e = cudaSuccess;
+#define B200_ATTN_EACH(F) F(true, 0) F(true, 1) F(true, 2) F(true, 3) F(true, 4) F(false, 0) F(false, 1) F(false, 2) F(false, 3) F(false, 4)
+#define B200_ATTN_SET(T, P) if (e == cudaSuccess) e = set_smem<T, P>();
+    B200_ATTN_EACH(B200_ATTN_SET)
+#undef B200_ATTN_SET
+    return e;
 }
 
 cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tctx, const int32_t* lens, int B, int S,
                              cudaStream_t stream, unsigned long long* dbg) {
     if (S < 1 || S > attn::MAX_KB * attn::KB || B < 1) return cudaErrorInvalidValue;
-    attn::attention_kernel<<<B * HEADS, attn::NUM_THREADS, attn::SMEM_BYTES, stream>>>(tq, tctx, lens, S, dbg);
+    const int variant = attention_variant();
+#define B200_ATTN_LAUNCH(T, P) if (variant == ((T) ? 0 : 5) + (P)) launch<T, P>(tq, tctx, lens, B, S, stream, dbg);
+    B200_ATTN_EACH(B200_ATTN_LAUNCH)
+#undef B200_ATTN_LAUNCH
+#undef B200_ATTN_EACH
     return cudaGetLastError();
 }
 
