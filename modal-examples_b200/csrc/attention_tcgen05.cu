@@ -39,45 +39,38 @@ constexpr int SB = 64;       // keys per sub-block
 constexpr int D = HEAD_DIM;  // 64
 constexpr int MAX_KB = 4;    // S <= 512
 constexpr int MAX_NQ = 4;
-constexpr int NSLOT = 4;     // TMEM S slots of 64 columns
-constexpr int NEXP = 2;      // exp warpgroups == P buffers == accumulators per tile
-constexpr uint32_t TM_O = 0;                // accumulators: (tile parity, warpgroup) -> 2 x NEXP x 64 columns
-constexpr uint32_t TM_S = 2 * NEXP * D;     // S ring: NSLOT x 64 columns
+constexpr int MAX_NEXP = 3;  // exp warpgroups == P buffers == accumulators per tile (template parameter NEXP: 2 or 3)
+constexpr uint32_t TM_O = 0;  // accumulators: (tile parity, warpgroup) -> 2 x NEXP x 64 columns; the S ring takes the rest
 constexpr int TILE_BYTES = 128 * D * 2;  // 16 KB: 128 rows x 128 B
-constexpr int OFF_Q = 0;                            // 2 x 16 KB (double buffered across tiles)
+constexpr int OFF_Q = 0;                            // 2 x 16 KB (double buffered across tiles); doubles as the epilogue's
+                                                    // staging tile once the tile's MMAs have retired
 constexpr int OFF_K = OFF_Q + 2 * TILE_BYTES;       // 4 x 16 KB
 constexpr int OFF_V = OFF_K + MAX_KB * TILE_BYTES;  // 4 x 16 KB
-constexpr int OFF_O = OFF_V + MAX_KB * TILE_BYTES;  // 16 KB: the epilogue's staging tile for the TMA store
-constexpr int OFF_LS = OFF_O + TILE_BYTES;          // float2 [MAX_NQ][NEXP][128]: (reference max, row sum) per tile and warpgroup
-constexpr int OFF_BAR = OFF_LS + MAX_NQ * NEXP * QT * 8;
+constexpr int OFF_LS = OFF_V + MAX_KB * TILE_BYTES; // float2 [MAX_NQ][MAX_NEXP][128]: (reference max, row sum) per tile and warpgroup
+constexpr int OFF_BAR = OFF_LS + MAX_NQ * MAX_NEXP * QT * 8;
 constexpr int OFF_P = (OFF_BAR + 512 + 1023) / 1024 * 1024;  // NEXP x 16 KB, 1024-aligned for the 128B swizzle
-static_assert(OFF_P % 1024 == 0 && OFF_O % 1024 == 0 && OFF_V % 1024 == 0, "swizzled tiles must be 1024-byte aligned");
-constexpr int SMEM_BYTES = OFF_P + NEXP * TILE_BYTES + 1024;
-constexpr int NUM_THREADS = 128 + NEXP * 128 + 128;
-constexpr int BAR_TOKEN = 1;             // named barriers 1 .. NEXP: MUFU token
-constexpr int BAR_EPI = 1 + NEXP;        // the epilogue warpgroup's own barrier
+static_assert(OFF_P % 1024 == 0 && OFF_V % 1024 == 0, "swizzled tiles must be 1024-byte aligned");
+constexpr int smem_bytes(int nexp) { return OFF_P + nexp * TILE_BYTES + 1024; }
+constexpr int num_threads(int nexp) { return 128 + nexp * 128 + 128; }
+static_assert(smem_bytes(MAX_NEXP) <= 232448, "shared memory");
+#ifdef B200_ATTN_NO_SETMAXNREG
+constexpr bool kRebalance = false;
+#else
+constexpr bool kRebalance = true;
+#endif
+constexpr int BAR_TOKEN = 1;               // named barriers 1 .. NEXP: MUFU token
+constexpr int BAR_EPI = 1 + MAX_NEXP;      // the epilogue warpgroup's own barrier
 
 // softmax_scale * log2(e) with softmax_scale = 1/sqrt(64)
 constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;
 // the reference max follows the true max only when it is exceeded by more than this (raw score units): P <= 2^8
 constexpr float kRescaleThreshold = 8.0f / kScaleLog2e;
 
-// 2^x for x <= ~8 on the FMA pipe: round-to-nearest split x = i + f, |f| <= 0.5, degree-3 minimax for 2^f (7.5e-5 relative,
-// well inside fp16's 4.9e-4), exponent added as an integer.  x is clamped at -126 (also maps a masked -inf to ~0).
-__device__ __forceinline__ float ex2_poly(float x) {
-    x = fmaxf(x, -126.0f);
-    const float t = x + 12582912.0f;  // 1.5 * 2^23: the integer part lands in the low mantissa bits
-    const float f = x - (t - 12582912.0f);
-    float p = fmaf(0.05517163872718811f, f, 0.2426111251115799f);
-    p = fmaf(p, f, 0.6932609677314758f);
-    p = fmaf(p, f, 0.9999280571937561f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
-// USE_TOKEN: the exp phases of the warpgroups take turns on the MUFU.  POLY: of every 8 scores, this many take ex2_poly
-// instead of MUFU.EX2 (a single warp's MUFU stream sustains one EX2 per ~11 cycles; the FMA pipe has slots to spare).
-template <bool USE_TOKEN, int POLY>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// NEXP exp warpgroups; USE_TOKEN: their exp phases take turns on the MUFU.  With NEXP = 3 the CTA has 640 threads (96
+// registers each at launch) and the warpgroups re-balance WITHIN that pool of 640 x 96: 120 for the exp warps, 80 for the
+// epilogue, 40 for the rest (asking for more than the launch allocation holds makes setmaxnreg.inc spin forever).
+template <int NEXP, bool USE_TOKEN>
+__global__ void __launch_bounds__(num_threads(NEXP), 1)
 attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tctx,
                  const int32_t* __restrict__ lens, int S, unsigned long long* __restrict__ dbg) {
     // dbg (diagnostics, normally NULL): CTA 0 records clock64() stamps; observer o in {exp WG 0..2, epilogue WG, P.V thread},
@@ -88,6 +81,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
     } while (0)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int NSLOT = 8 - 2 * NEXP;              // TMEM S slots of 64 columns: 4 or 2
+    constexpr uint32_t TM_S = 2 * NEXP * D;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
     uint64_t* k_full = bars + 0;
     uint64_t* v_full = bars + 1;
@@ -95,10 +90,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
     uint64_t* q_empty = bars + 4;      // [2]
     uint64_t* o_done = bars + 6;       // [2]  the tile's last P.V has retired
     uint64_t* o_free = bars + 8;       // [2]  the epilogue has read the accumulator
-    uint64_t* s_full = bars + 10;      // [NSLOT]  S_c landed in slot c&3
-    uint64_t* s_free = bars + 14;      // [NSLOT]  S_c is in the exp warpgroup's registers
-    uint64_t* p_full = bars + 18;      // [NEXP]  P buffer w written
-    uint64_t* pv_done = bars + 22;     // [NEXP]  the P.V reading P buffer w has retired
+    // S_c lives in TMEM slot c % NSLOT but signals on barrier c % NRING, NRING = lcm(NSLOT, NEXP): each barrier then has a
+    // single waiter that meets its phases in order (with 2 slots and 3 warpgroups a warpgroup's first wait would
+    // otherwise be for phase 1 of a barrier whose phase 0 it never saw, and pass at once)
+    constexpr int NRING = NEXP == 3 ? 6 : 4;
+    uint64_t* s_full = bars + 10;      // [NRING]  S_c landed
+    uint64_t* s_free = bars + 16;      // [NRING]  S_c is in the exp warpgroup's registers
+    uint64_t* p_full = bars + 22;      // [NEXP]  P buffer w written
+    uint64_t* pv_done = bars + 25;     // [NEXP]  the P.V reading P buffer w has retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
 
     const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
@@ -125,7 +124,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             mbar_init(&o_done[i], 1);
             mbar_init(&o_free[i], 128);
         }
-        for (int i = 0; i < NSLOT; ++i) {
+        for (int i = 0; i < NRING; ++i) {
             mbar_init(&s_full[i], 1);
             mbar_init(&s_free[i], 128);
         }
@@ -141,7 +140,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    // (each role's code must be dominated by its own setmaxnreg for ptxas to allocate against the new budget)
+    if (warp < 4) {
+      if constexpr (NEXP == 3 && kRebalance) setmaxnreg_dec<40>();
+      if (warp == 0) {
         if (elect_one()) {
             // ------------------------------------------------------------ TMA producer
             for (int t = 0; t < nq && t < 2; ++t) {
@@ -156,12 +158,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 tma_load_3d(smem + OFF_V + j * TILE_BYTES, &tq, v_full, 2 * HIDDEN + h * D, j * KB, b);
             for (int t = 2; t < nq; ++t) {
                 const int qb = t & 1;
-                mbar_wait(&q_empty[qb], ((t >> 1) - 1) & 1);  // tile t-2's S MMAs have retired
+                mbar_wait(&q_empty[qb], ((t >> 1) - 1) & 1);  // tile t-2 has left the buffer (epilogue)
                 mbar_arrive_expect_tx(&q_full[qb], TILE_BYTES);
                 tma_load_3d(smem + OFF_Q + qb * TILE_BYTES, &tq, &q_full[qb], h * D, t * QT, b);
             }
         }
-    } else if (warp == 1) {
+      } else if (warp == 1) {
         if (elect_one()) {
             // ------------------------------------------------------------ S issuer: S_c = Q . K_c^T into S slot c&3
             constexpr uint32_t idesc_s = make_idesc_f16(QT, SB);  // 128 x 64, both K-major
@@ -172,22 +174,21 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             for (int c = 0; c < total; ++c) {  // runs as far ahead as free slots allow
                 const uint32_t slot = c & (NSLOT - 1);
                 if (sb == 0) mbar_wait(&q_full[t & 1], (t >> 1) & 1);
-                if (c >= NSLOT) mbar_wait(&s_free[slot], ((c / NSLOT) - 1) & 1);
+                if (c >= NSLOT) mbar_wait(&s_free[(c - NSLOT) % NRING], ((c - NSLOT) / NRING) & 1);  // the slot's previous S
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < D / 16; ++k) {
                     umma_f16_ss(tmem_base + TM_S + slot * SB, make_sw128_desc(q_addr + (t & 1) * TILE_BYTES + k * 32),
                                 make_sw128_desc(k_addr + sb * (SB * 128) + k * 32), idesc_s, k != 0);
                 }
-                umma_commit(&s_full[slot]);
+                umma_commit(&s_full[c % NRING]);
                 if (++sb == nsb) {
-                    umma_commit(&q_empty[t & 1]);  // this tile's Q is no longer needed once these retire
                     sb = 0;
                     ++t;
                 }
             }
         }
-    } else if (warp == 3) {
+      } else if (warp == 3) {
         if (elect_one()) {
             // ------------------------------------------------------------ P.V issuer: O_{t,w} (+)= P_c . V_c, w = c mod NEXP
             constexpr uint32_t idesc_o = make_idesc_f16(QT, D, 0, 1);  // 128 x 64, B (= V) MN-major
@@ -223,8 +224,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 }
             }
         }
-    } else if (warp >= 4 && warp < 4 + 4 * NEXP) {
+      }
+    } else if (warp < 4 + 4 * NEXP) {
         // ---------------------------------------------------------------- exp warpgroup w: sub-blocks c = w (mod NEXP)
+        if constexpr (NEXP == 3 && kRebalance) setmaxnreg_inc<120>();
         const int w = (warp - 4) >> 2;
         const int r = (warp & 3) * 32 + lane;  // query row within the tile == TMEM lane
         const uint32_t tm = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
@@ -244,7 +247,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
         for (int c = w; c < total; c += NEXP, ++use) {
             const uint32_t slot = c & (NSLOT - 1);
             if (obs) ATT_STAMP(w, c, 0);
-            mbar_wait(&s_full[slot], (c / NSLOT) & 1);
+            mbar_wait(&s_full[c % NRING], (c / NRING) & 1);
             tc_fence_after();
             if (obs) ATT_STAMP(w, c, 1);
             const int valid = len - sb * SB;  // keys [0, valid) of this sub-block are real (>= 1)
@@ -289,7 +292,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 load_scores();
             }
             tc_fence_before();
-            mbar_arrive(&s_free[slot]);  // the scores live in registers from here on
+            mbar_arrive(&s_free[c % NRING]);  // the scores live in registers from here on
             const float neg_ms = -m_ref * kScaleLog2e;
             if (use > 0) mbar_wait(&pv_done[w], (use - 1) & 1);  // the previous P of this buffer has been consumed
             if (USE_TOKEN) named_bar_sync(BAR_TOKEN + w, 256);
@@ -302,9 +305,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 for (int e = 0; e < 4; ++e) {
                     const float x0 = fmaf(__uint_as_float(v[q * 8 + 2 * e]), kScaleLog2e, neg_ms);
                     const float x1 = fmaf(__uint_as_float(v[q * 8 + 2 * e + 1]), kScaleLog2e, neg_ms);
-                    // POLY of each 8 go to the FMA pipe, spread over the 8 so that they fill the MUFU's shadow
-                    const float p0 = (POLY >= 3 && e == 1) || (POLY >= 4 && e == 3) ? ex2_poly(x0) : ex2_approx(x0);
-                    const float p1 = (POLY >= 1 && e == 3) || (POLY >= 2 && e == 1) ? ex2_poly(x1) : ex2_approx(x1);
+                    const float p0 = ex2_approx(x0);
+                    const float p1 = ex2_approx(x1);
                     ls0 += p0;
                     ls1 += p1;
                     pk[e] = pack_half2(p0, p1);
@@ -315,7 +317,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             if (USE_TOKEN) named_bar_arrive(BAR_TOKEN + (w + 1 == NEXP ? 0 : w + 1), 256);  // MUFU to the next warpgroup
             l_w += ls0 + ls1;
             if (sb + NEXP >= nsb)  // this warpgroup's last sub-block of the tile
-                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(ls_self + t * (NEXP * QT * 8)), "f"(m_ref), "f"(l_w) : "memory");
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(ls_self + t * (MAX_NEXP * QT * 8)), "f"(m_ref), "f"(l_w) : "memory");
             tc_fence_before();         // our TMEM accesses precede the MMA that accumulates into O_t
             fence_proxy_async_smem();  // P_c visible to the tensor core's async-proxy reads
             mbar_arrive(&p_full[w]);   // (release: also publishes (m, l) to the epilogue via the o_done chain)
@@ -326,12 +328,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 ++t;
             }
         }
-    } else if (warp >= 4 + 4 * NEXP) {
+    } else {
         // ---------------------------------------------------------------- epilogue warpgroup: ctx = O_t / l
+        if constexpr (NEXP == 3 && kRebalance) setmaxnreg_dec<80>();
         const int r = (warp & 3) * 32 + lane;
         const uint32_t tm = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
         const uint32_t ls_base = smem_u32(smem + OFF_LS) + r * 8;
-        const uint32_t o_row = smem_u32(smem + OFF_O) + r * 128;
         const uint32_t swz = static_cast<uint32_t>(r & 7);
         const bool obs = (warp & 3) == 0 && lane == 0;
 #pragma unroll 1
@@ -351,7 +353,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 m_w[w] = -INFINITY;
                 l_w[w] = 0.f;
                 if (part_w[w]) {
-                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_w[w]), "=f"(l_w[w]) : "r"(ls_base + (t * NEXP + w) * (QT * 8)) : "memory");
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_w[w]), "=f"(l_w[w]) : "r"(ls_base + (t * MAX_NEXP + w) * (QT * 8)) : "memory");
                     m_fin = fmaxf(m_fin, m_w[w]);
                 }
             }
@@ -364,9 +366,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             const float inv_l = 1.0f / l_fin;
 #pragma unroll
             for (int w = 0; w < NEXP; ++w) f_w[w] *= inv_l;
-            // the previous tile's TMA store has finished reading the staging tile
-            if (warp == 4 + 4 * NEXP && lane == 0) tma_store_wait_read<0>();
-            named_bar_sync(BAR_EPI, 128);
+            // staging tile = this tile's Q buffer: all of the tile's MMAs have retired (o_done), and tile t+2's Q is only
+            // loaded into it once our TMA store has read it back out (q_empty below)
+            const uint32_t o_row = smem_u32(smem + OFF_Q + (t & 1) * TILE_BYTES) + r * 128;
 #pragma unroll
             for (int part = 0; part < D / 32; ++part) {
                 float acc[32];
@@ -396,12 +398,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             fence_proxy_async_smem();
             named_bar_sync(BAR_EPI, 128);
             if (warp == 4 + 4 * NEXP && lane == 0) {  // rows past S are clipped by the tensor map
-                tma_store_3d(&tctx, smem + OFF_O, h * D, t * QT, b);
+                tma_store_3d(&tctx, smem + OFF_Q + (t & 1) * TILE_BYTES, h * D, t * QT, b);
                 tma_store_commit();
+                tma_store_wait_read<0>();
+                mbar_arrive(&q_empty[t & 1]);
             }
             if (obs) ATT_STAMP(3, t, 2);
         }
-        if (warp == 4 + 4 * NEXP && lane == 0) tma_store_wait_read<0>();  // shared memory must outlive the last store's reads
     }
 
     tc_fence_before();
@@ -415,45 +418,45 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
 }  // namespace attn
 
 namespace {
-// diagnostics: B200RT_ATTN_VARIANT = "<t|n><0..4>": exp phases take turns on the MUFU (t) or overlap freely (n), and how many
-// of every 8 exponentials run as a polynomial on the FMA pipe.  The product default is the fastest measured combination.
-constexpr int kDefaultVariant = 0 * 5 + 0;  // token, POLY 0
+// diagnostics: B200RT_ATTN_VARIANT = "<2|3><t|n>": number of exp warpgroups, and whether their exp phases take turns on the
+// MUFU (t) or overlap freely (n).  The product default is the fastest measured combination.
+constexpr int kDefaultVariant = 0;  // 2t
 int attention_variant() {
     static const int v = [] {
         const char* e = getenv("B200RT_ATTN_VARIANT");
-        if (!e || (e[0] != 't' && e[0] != 'n') || e[1] < '0' || e[1] > '4') return kDefaultVariant;
-        return (e[0] == 'n' ? 5 : 0) + (e[1] - '0');
+        if (!e || (e[0] != '2' && e[0] != '3') || (e[1] != 't' && e[1] != 'n')) return kDefaultVariant;
+        return (e[0] == '3' ? 2 : 0) + (e[1] == 'n' ? 1 : 0);
     }();
     return v;
 }
-template <bool TOKEN, int POLY>
+template <int NEXP, bool TOKEN>
 cudaError_t set_smem() {
-    return cudaFuncSetAttribute(attn::attention_kernel<TOKEN, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::SMEM_BYTES);
+    return cudaFuncSetAttribute(attn::attention_kernel<NEXP, TOKEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn::smem_bytes(NEXP));
 }
-template <bool TOKEN, int POLY>
+template <int NEXP, bool TOKEN>
 void launch(const CUtensorMap& tq, const CUtensorMap& tctx, const int32_t* lens, int B, int S, cudaStream_t stream,
             unsigned long long* dbg) {
-    attn::attention_kernel<TOKEN, POLY><<<B * HEADS, attn::NUM_THREADS, attn::SMEM_BYTES, stream>>>(tq, tctx, lens, S, dbg);
+    attn::attention_kernel<NEXP, TOKEN><<<B * HEADS, attn::num_threads(NEXP), attn::smem_bytes(NEXP), stream>>>(tq, tctx, lens, S, dbg);
 }
 }  // namespace
 
 cudaError_t attention_init_device() {
-    cudaError_t e = cudaSuccess;
-#define B200_ATTN_EACH(F) F(true, 0) F(true, 1) F(true, 2) F(true, 3) F(true, 4) F(false, 0) F(false, 1) F(false, 2) F(false, 3) F(false, 4)
-#define B200_ATTN_SET(T, P) if (e == cudaSuccess) e = set_smem<T, P>();
-    B200_ATTN_EACH(B200_ATTN_SET)
-#undef B200_ATTN_SET
+    cudaError_t e = set_smem<2, true>();
+    if (e == cudaSuccess) e = set_smem<2, false>();
+    if (e == cudaSuccess) e = set_smem<3, true>();
+    if (e == cudaSuccess) e = set_smem<3, false>();
     return e;
 }
 
 cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tctx, const int32_t* lens, int B, int S,
                              cudaStream_t stream, unsigned long long* dbg) {
     if (S < 1 || S > attn::MAX_KB * attn::KB || B < 1) return cudaErrorInvalidValue;
-    const int variant = attention_variant();
-#define B200_ATTN_LAUNCH(T, P) if (variant == ((T) ? 0 : 5) + (P)) launch<T, P>(tq, tctx, lens, B, S, stream, dbg);
-    B200_ATTN_EACH(B200_ATTN_LAUNCH)
-#undef B200_ATTN_LAUNCH
-#undef B200_ATTN_EACH
+    switch (attention_variant()) {
+        case 1: launch<2, false>(tq, tctx, lens, B, S, stream, dbg); break;
+        case 2: launch<3, true>(tq, tctx, lens, B, S, stream, dbg); break;
+        case 3: launch<3, false>(tq, tctx, lens, B, S, stream, dbg); break;
+        default: launch<2, true>(tq, tctx, lens, B, S, stream, dbg); break;
+    }
     return cudaGetLastError();
 }
 
