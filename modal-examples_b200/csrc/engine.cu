@@ -1095,7 +1095,7 @@ int b200rt_debug_attention(const uint16_t* qkv, const int32_t* lens, uint16_t* c
         unsigned long long t0 = ~0ull;
         for (auto v : hs) if (v && v < t0) t0 = v;
         if (FILE* f = fopen(path, "w")) {
-            const char* names[5] = {"exp_wg0", "exp_wg1", "exp_wg2", "fold", "mma"};
+            const char* names[5] = {"exp_wg0", "exp_wg1", "exp_wg2", "epilogue", "pv"};
             for (int o = 0; o < 5; ++o)
                 for (int c = 0; c < 32; ++c) {
                     bool any = false;
