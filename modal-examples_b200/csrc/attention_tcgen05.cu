@@ -72,7 +72,7 @@ constexpr float kRescaleThreshold = 8.0f / kScaleLog2e;
 template <int NEXP, bool USE_TOKEN>
 __global__ void __launch_bounds__(num_threads(NEXP), 1)
 attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tctx,
-                 const int32_t* __restrict__ lens, int S, unsigned long long* __restrict__ dbg) {
+                 const int32_t* __restrict__ lens, int S, int split, unsigned long long* __restrict__ dbg) {
     // dbg (diagnostics, normally NULL): CTA 0 records clock64() stamps; observer o in {exp WG 0..2, epilogue WG, P.V thread},
     // 32 sub-blocks x 8 slots each (tools/attn_timeline.py prints them)
 #define ATT_STAMP(o, c, slot)                                                                          \
@@ -98,11 +98,19 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
 
     const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
     const int lane = lane_id();
-    const int b = blockIdx.x / HEADS;
-    const int h = blockIdx.x % HEADS;
+    // split != 0 (small batches): one CTA per (item, head, query tile) instead of per (item, head) -- K and V are then
+    // loaded once per tile, but a single item spreads over 48 SMs instead of 12
+    const int nq_all = (S + QT - 1) / QT;
+    int unit = blockIdx.x, t0 = 0;
+    if (split) {
+        t0 = unit % nq_all;
+        unit /= nq_all;
+    }
+    const int b = unit / HEADS;
+    const int h = unit % HEADS;
     int len = lens[b];
     len = len < 1 ? 1 : (len > S ? S : len);
-    const int nq = (S + QT - 1) / QT;
+    const int nq = split ? 1 : nq_all;    // query tiles of this CTA: t0 .. t0 + nq - 1
     const int nsb = (len + SB - 1) / SB;  // valid 64-key sub-blocks per tile
     const int nkb = (nsb + 1) / 2;        // 128-key K/V tiles holding them
     const int total = nq * nsb;           // the CTA's stream of sub-blocks
@@ -144,7 +152,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             // ------------------------------------------------------------ TMA producer
             for (int t = 0; t < nq && t < 2; ++t) {
                 mbar_arrive_expect_tx(&q_full[t], TILE_BYTES);
-                tma_load_3d(smem + OFF_Q + t * TILE_BYTES, &tq, &q_full[t], h * D, t * QT, b);
+                tma_load_3d(smem + OFF_Q + t * TILE_BYTES, &tq, &q_full[t], h * D, (t0 + t) * QT, b);
             }
             mbar_arrive_expect_tx(k_full, nkb * TILE_BYTES);
             for (int j = 0; j < nkb; ++j)
@@ -156,7 +164,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 const int qb = t & 1;
                 mbar_wait(&q_empty[qb], ((t >> 1) - 1) & 1);  // tile t-2 has left the buffer (epilogue)
                 mbar_arrive_expect_tx(&q_full[qb], TILE_BYTES);
-                tma_load_3d(smem + OFF_Q + qb * TILE_BYTES, &tq, &q_full[qb], h * D, t * QT, b);
+                tma_load_3d(smem + OFF_Q + qb * TILE_BYTES, &tq, &q_full[qb], h * D, (t0 + t) * QT, b);
             }
         }
       } else if (warp == 1) {
@@ -392,7 +400,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             fence_proxy_async_smem();
             named_bar_sync(BAR_EPI, 128);
             if (warp == 4 + 4 * NEXP && lane == 0) {  // rows past S are clipped by the tensor map
-                tma_store_3d(&tctx, smem + OFF_Q + (t & 1) * TILE_BYTES, h * D, t * QT, b);
+                tma_store_3d(&tctx, smem + OFF_Q + (t & 1) * TILE_BYTES, h * D, (t0 + t) * QT, b);
                 tma_store_commit();
                 tma_store_wait_read<0>();
                 mbar_arrive(&q_empty[t & 1]);
@@ -430,7 +438,11 @@ cudaError_t set_smem() {
 template <int NEXP, bool TOKEN>
 void launch(const CUtensorMap& tq, const CUtensorMap& tctx, const int32_t* lens, int B, int S, cudaStream_t stream,
             unsigned long long* dbg) {
-    attn::attention_kernel<NEXP, TOKEN><<<B * HEADS, attn::num_threads(NEXP), attn::smem_bytes(NEXP), stream>>>(tq, tctx, lens, S, dbg);
+    // fewer (item, head) units than SMs: split them by query tile (diagnostic stamps keep the unsplit layout)
+    const int nq = (S + attn::QT - 1) / attn::QT;
+    const int split = (B * HEADS < 148 && nq > 1 && dbg == nullptr) ? 1 : 0;
+    attn::attention_kernel<NEXP, TOKEN><<<B * HEADS * (split ? nq : 1), attn::num_threads(NEXP), attn::smem_bytes(NEXP), stream>>>(
+        tq, tctx, lens, S, split, dbg);
 }
 }  // namespace
 
