@@ -84,6 +84,35 @@ def test_attention_kernel_vs_numpy(rt, B, S, lens):
     assert (np.abs(got - ref) <= 4e-3 * np.abs(ref) + 4e-3).all()  # P and ctx are rounded to fp16
 
 
+def _ref_attention(qkv, lens, B, S):
+    q = qkv.astype(np.float64).reshape(B, S, 3, 12, 64)
+    qq, kk, vv = (q[:, :, j].transpose(0, 2, 1, 3) for j in range(3))
+    s = (qq @ kk.transpose(0, 1, 3, 2)) * 0.125
+    s = np.where((np.arange(S)[None, :] >= np.array(lens)[:, None])[:, None, None, :], -np.inf, s)
+    e = np.exp(s - s.max(-1, keepdims=True))
+    return ((e / e.sum(-1, keepdims=True)) @ vv).transpose(0, 2, 1, 3).reshape(B * S, 768)
+
+
+@pytest.mark.parametrize("B,S,lens", [(2, 512, [512, 300]), (13, 512, [512] * 12 + [77])])
+def test_attention_running_max_rescale(rt, B, S, lens):
+    """Scores that climb by more than the kernel's 2^8 lazy-rescale threshold from one 64-key sub-block to the next
+    (for the rows whose query points along u; they fall for the others), so that the in-TMEM accumulator rescale runs at
+    every sub-block for part of each warp.  B = 2 takes the query-tile-split launch, B = 13 the one-CTA-per-head launch."""
+    rng = np.random.default_rng(7 * B + S)
+    x = rng.standard_normal((B, S, 3, 12, 64)) * 0.5
+    u = rng.standard_normal(64)
+    u /= np.linalg.norm(u)
+    sign = np.where(rng.random((B, S, 12, 1)) < 0.6, 1.0, -1.0)
+    x[:, :, 0] += 4.0 * sign * u                                          # q . u = +-4
+    x[:, :, 1] += (12.0 * (np.arange(S) // 64))[None, :, None, None] * u  # k . u = 12 * sub-block: raw q.k steps by 48 > 44.4
+    qkv = x.reshape(B * S, 2304).astype(np.float16)
+    ctx, _ = rt.debug_attention(qkv, np.array(lens, np.int32), B, S)
+    ref = _ref_attention(qkv, lens, B, S)
+    got = ctx.astype(np.float64)
+    assert np.isfinite(got).all()
+    assert (np.abs(got - ref) <= 4e-3 * np.abs(ref) + 4e-3).all()
+
+
 def test_hidden_states_layer_by_layer(rt):
     g, flat, model = get_model(rt, 2, "trained", 3)
     ids, lens = R.synth_ragged(3, 200, seed=5, min_len=3)
