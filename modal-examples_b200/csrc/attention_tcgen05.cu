@@ -114,6 +114,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
     const int nsb = (len + SB - 1) / SB;  // valid 64-key sub-blocks per tile
     const int nkb = (nsb + 1) / 2;        // 128-key K/V tiles holding them
     const int total = nq * nsb;           // the CTA's stream of sub-blocks
+    // Sub-block c of this CTA is the item's sub-block t0 nsb + c and goes to warpgroup (c_off + c) % NEXP: the split launch
+    // gives every sub-block to the warpgroup the unsplit one would (the row sums are grouped by warpgroup, so that an
+    // item's embedding is bit-identical in any batch)
+    const int c_off = (t0 * nsb) % NEXP;
 
     if (warp == 0 && elect_one()) {
         prefetch_tmap(&tq);
@@ -200,10 +204,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             const uint32_t p_addr = smem_u32(smem + OFF_P);
             if (total > 0) mbar_wait(v_full, 0);
             int t = 0, sb = 0;
-            uint32_t pb = 0, use = 0;
+            uint32_t pb = c_off, phases = 0;  // bit w of phases: parity of the phase of p_full[w] awaited next
             for (int c = 0; c < total; ++c) {
                 ATT_STAMP(4, c, 0);
-                mbar_wait(&p_full[pb], use & 1);
+                mbar_wait(&p_full[pb], (phases >> pb) & 1);
+                phases ^= 1u << pb;
                 if (sb == 0 && t >= 2) mbar_wait(&o_free[t & 1], ((t >> 1) - 1) & 1);  // tile t-2 has been written out
                 tc_fence_after();
                 ATT_STAMP(4, c, 1);
@@ -221,10 +226,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                     sb = 0;
                     ++t;
                 }
-                if (++pb == NEXP) {
-                    pb = 0;
-                    ++use;
-                }
+                if (++pb == NEXP) pb = 0;
             }
         }
       }
@@ -241,16 +243,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
         const uint32_t ls_self = smem_u32(smem + OFF_LS) + (w * QT + r) * 8;
         const uint32_t swz = static_cast<uint32_t>(r & 7);
         const bool obs = (warp & 3) == 0 && lane == 0;
-        int t = 0, sb = w;
+        int t = 0, sb = (w + NEXP - c_off) % NEXP;
         while (sb >= nsb) {
             sb -= nsb;
             ++t;
         }
         float l_w = 0.f, m_ref = 0.f;  // this warpgroup's partial row sum of the tile, relative to m_ref
         uint32_t use = 0;              // how often this warpgroup's P buffer has been filled
-        if (USE_TOKEN && w == NEXP - 1) named_bar_arrive(BAR_TOKEN, 256);  // warpgroup 0 goes first
+        const int c_first_w = (w + NEXP - c_off) % NEXP;    // this warpgroup's first sub-block
+        const int c_first_wp = (wp + NEXP - c_off) % NEXP;  // ... and its predecessor's
+        if (USE_TOKEN && w == (c_off + NEXP - 1) % NEXP) named_bar_arrive(BAR_TOKEN + c_off, 256);  // warpgroup c_off goes first
 #pragma unroll 1
-        for (int c = w; c < total; c += NEXP, ++use) {
+        for (int c = c_first_w; c < total; c += NEXP, ++use) {
             const uint32_t slot = c % NSLOT;
             if (obs) ATT_STAMP(w, c, 0);
             mbar_wait(&s_full[c % NRING], (c / NRING) & 1);
@@ -295,7 +299,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 // Our own previous P.V first (its barrier's phases are met in order), then sub-block c-1's: its
                 // predecessor on that barrier was issued before ours and has therefore retired too.
                 if (use > 0) mbar_wait(&pv_done[w], (use - 1) & 1);
-                mbar_wait(&pv_done[wp], ((c - 1) / NEXP) & 1);  // O_t is complete up to sub-block c-1
+                mbar_wait(&pv_done[wp], ((c - 1 - c_first_wp) / NEXP) & 1);  // O_t is complete up to sub-block c-1
                 tc_fence_after();
                 const float f = ex2_approx((m_prev - m_used) * kScaleLog2e);
                 const uint32_t o_addr = tm + TM_O + (t & 1) * D;
@@ -362,7 +366,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             tc_fence_after();
             if (obs) ATT_STAMP(3, t, 1);
             // l = sum of the warpgroups' partial row sums brought to the tile's final reference max (the last sub-block's)
-            const int c_first = t * nsb;
+            const int c_first = (t0 + t) * nsb;  // (item-wide index: decides which warpgroup had which sub-block)
             const int w_last = (c_first + nsb - 1) % NEXP;
             float m_fin, l_fin;
             asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(m_fin), "=f"(l_fin) : "r"(ls_base + (t * MAX_NEXP + w_last) * (QT * 8)) : "memory");
@@ -440,7 +444,8 @@ void launch(const CUtensorMap& tq, const CUtensorMap& tctx, const int32_t* lens,
             unsigned long long* dbg) {
     // fewer (item, head) units than SMs: split them by query tile (diagnostic stamps keep the unsplit layout)
     const int nq = (S + attn::QT - 1) / attn::QT;
-    const int split = (B * HEADS < 148 && nq > 1 && dbg == nullptr) ? 1 : 0;
+    static const bool no_split = getenv("B200RT_ATTN_NOSPLIT") != nullptr;  // diagnostics
+    const int split = (B * HEADS < 148 && nq > 1 && dbg == nullptr && !no_split) ? 1 : 0;
     attn::attention_kernel<NEXP, TOKEN><<<B * HEADS * (split ? nq : 1), attn::num_threads(NEXP), attn::smem_bytes(NEXP), stream>>>(
         tq, tctx, lens, S, split, dbg);
 }
