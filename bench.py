@@ -319,10 +319,10 @@ def main_ours(args):
     one_ids = pin_ids.array[:1]
     one_out = pin_out.array[:1]
     lat = []
-    for i in range(120):
+    for i in range(1100):  # 1 000 trials after 100 warm-ups
         t1 = time.perf_counter()
         model.wait(model.submit(one_ids, None, out=one_out))
-        if i >= 20:
+        if i >= 100:
             lat.append((time.perf_counter() - t1) * 1e3)
     lat.sort()
     p50_ms, p99_ms = lat[len(lat) // 2], lat[int(len(lat) * 0.99) - 1]
@@ -382,7 +382,7 @@ def main_ours(args):
                     "device_resident_rerun_after_e2e": total_items / (dev_ms_after / 1e3),
                     "per_step_ms": {k: (s1[k] - s0[k]) / args.steps / 1e3 for k in ("stage_us", "h2d_scatter_us", "forward_us", "gap_us", "d2h_us")}},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "latency": {"p50_ms": p50_ms, "p99_ms": p99_ms, "what": "one 512-token item, b200rt_submit+b200rt_wait, pinned host buffers, 100 trials after 20 warm-ups (rank 0)"},
+            "latency": {"p50_ms": p50_ms, "p99_ms": p99_ms, "what": "one 512-token item, b200rt_submit+b200rt_wait, pinned host buffers, 1000 trials after 100 warm-ups (rank 0)"},
         }
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
