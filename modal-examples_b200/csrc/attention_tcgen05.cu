@@ -25,6 +25,10 @@
 // Keys >= len are masked to -inf before the max (exactly P = 0, matching HF's additive -inf mask); sub-blocks wholly
 // past len are skipped.  k = log2(e) / sqrt(64).
 //
+// Batches with fewer (item, head) units than SMs launch one CTA per (item, head, query tile) instead.  Either way sub-block
+// c of tile t goes to warpgroup (t nsb + c) mod NEXP and sees the same reference maxima, so the output does not depend
+// on the launch shape: an item's embedding is bit-identical in any batch (tests: scheduler / size-independent properties).
+//
 // Restates BertSelfAttention.forward (HF modeling_bert.py:143-207) for the TEI /embed path the
 // reference calls at 06_gpu_and_ml/embeddings/text_embeddings_inference.py:100.
 #include <cstdlib>
