@@ -1,6 +1,7 @@
 """diagnostics: where does a forward with the query-tile-split attention launch differ from the unsplit one?"""
 import sys, os
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/modal-examples_b200')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'modal-examples_b200'))
 import numpy as np, b200rt
 from oracle import bge_ref as R
 b200rt.init(devices=[0])
