@@ -186,7 +186,7 @@ def main_reference(args):
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"bge-base-en-v1.5 embed, {SEQ}-token synthetic items, CPU oracle port of the TEI /embed path", "seq_len": SEQ,
                    "items_per_step": REF_ITEMS_PER_STEP},
-        "cpu_baseline": {"value": value, "unit": "items/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "items/s", "cores": threads, "host_cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "items/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     GUARD.emit(json.dumps(line))
@@ -194,6 +194,56 @@ def main_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+
+
+def _load_example():
+    """examples/embed_bge_native.py (the reference script with TEI replaced by the engine): its `TextEmbeddings` class is
+    what `e2e_map` drives through the `modal` shim's Function.map."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("embed_bge_native", os.path.join(ROOT, "examples", "embed_bge_native.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def run_independent_replicas(args, rank, local_rank, world, barrier, R):
+    """N > 1 only, secondary figure: every rank drives its own 1-replica pool on its own GPU (no scatter, no gather, no
+    shared dispatcher) -- the trivially parallel deployment the single-root pool is compared with."""
+    import torch
+    import b200rt
+
+    steps = max(3, args.steps // 4)
+    b200rt.init(devices=[local_rank])
+    model = b200rt.EmbedModel(R.geometry_dict(R.BGE_BASE), R.pack_blob(R.make_weights(R.BGE_BASE, 0, "hf"), R.BGE_BASE))
+    cap = b200rt.wave_capacity_items()
+    n_step = ITEMS_PER_STEP
+    with torch.cuda.device(local_rank):
+        d_ids = torch.from_numpy(R.synth_ids(n_step, SEQ, seed=rank)).cuda()
+        d_lens = torch.full((n_step,), SEQ, dtype=torch.int32, device="cuda")
+        d_out = torch.empty((n_step, 768), dtype=torch.float32, device="cuda")
+        ts = torch.cuda.Stream()
+
+        def device_step():
+            for i in range(0, n_step, cap):
+                model.embed_device(0, d_ids[i:].data_ptr(), d_lens[i:].data_ptr(), min(cap, n_step - i), SEQ, d_out[i:].data_ptr(), ts.cuda_stream)
+
+        with torch.cuda.stream(ts):
+            for _ in range(args.warmup):
+                device_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(ts):
+            e0.record()
+            for _ in range(steps):
+                device_step()
+            e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+    del d_ids, d_lens, d_out
+    b200rt.shutdown()
+    torch.cuda.empty_cache()
+    return ms, steps
 
 
 def main_ours(args):
@@ -207,113 +257,206 @@ def main_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback for the CUDA path (use --impl reference for the CPU arm)")
+    N = args.gpus
+    if torch.cuda.device_count() < N:
+        raise SystemExit(f"--gpus {N} but only {torch.cuda.device_count()} visible")
     torch.cuda.set_device(local_rank)
     use_dist = world > 1
+    host_pg = None
     if use_dist:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # Long waits (ranks > 0 idle while rank 0 drives the pool) go through a gloo group: an NCCL barrier spins a kernel
+        # on every waiting rank's GPU, which would time-slice against the pool's replicas on the same GPUs.
+        host_pg = dist.new_group(backend="gloo")
 
     def barrier():
         if use_dist:
             dist.barrier()
         torch.cuda.synchronize()
 
-    b200rt.init(devices=[local_rank])
+    def host_barrier():
+        if use_dist:
+            dist.barrier(group=host_pg)
+
+    # ---------------- N > 1, secondary: independent 1-replica pools, one per rank (the round-1 deployment)
+    indep = None
+    if use_dist:
+        ms, isteps = run_independent_replicas(args, rank, local_rank, world, barrier, R)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks, device time
+        indep = {"value": isteps * ITEMS_PER_STEP * world / (float(t[0]) / 1e3), "unit": "items/s", "steps": isteps,
+                 "what": "one process per GPU, each a 1-replica pool on its own shard, ids resident (no scatter/gather, peer_bytes 0)"}
+        torch.cuda.synchronize()
+    host_barrier()
+    if rank != 0:
+        # ---------------- ranks > 0: the pool is ONE process (rank 0) driving all N replicas; hold the barrier only
+        host_barrier()
+        dist.destroy_process_group()
+        return 0
+
+    # ================= rank 0: ONE pool of N replicas (scatter kernel -> peer HBM, fused peer gather, one dispatcher)
+    b200rt.init(N)
     g = R.BGE_BASE
     flat = R.make_weights(g, 0, "hf")
     model = b200rt.EmbedModel(R.geometry_dict(g), R.pack_blob(flat, g))
     del flat
     cap = b200rt.wave_capacity_items()
-    n_step = ITEMS_PER_STEP
-    ids_host = R.synth_ids(n_step, SEQ, seed=rank)  # every rank embeds its own shard of the corpus
+    n_step = ITEMS_PER_STEP                      # per GPU
+    n_total = n_step * N                         # per step, whole pool
+    ids_host = np.concatenate([R.synth_ids(n_step, SEQ, seed=r) for r in range(N)])  # replica r's shard has seed r
     peaks = load_peaks()
 
-    # ---------------- value: device-resident
-    d_ids = torch.from_numpy(ids_host).cuda()
-    d_lens = torch.full((n_step,), SEQ, dtype=torch.int32, device="cuda")
-    d_out = torch.empty((n_step, 768), dtype=torch.float32, device="cuda")
-    # A dedicated (non-default) torch stream: the forwards are enqueued on it and the CUDA events that time them are
-    # recorded on it.  (torch's default stream has handle 0, which b200rt_embed_device reads as "use the replica's own
-    # stream" -- events on the default stream would then not bracket the work.)
-    tstream = torch.cuda.Stream()
-    stream = tstream.cuda_stream
-    assert stream != 0
+    # ---------------- value: device-resident (each replica's shard already in its HBM), one enqueueing thread per replica
+    dev = []
+    for r in range(N):
+        with torch.cuda.device(r):
+            d = {"ids": torch.from_numpy(ids_host[r * n_step:(r + 1) * n_step]).cuda(),
+                 "lens": torch.full((n_step,), SEQ, dtype=torch.int32, device="cuda"),
+                 "out": torch.empty((n_step, 768), dtype=torch.float32, device="cuda"),
+                 # a dedicated (non-default) stream: the forwards are enqueued on it and the events that time them are
+                 # recorded on it (handle 0 would mean "the replica's own stream" to b200rt_embed_device)
+                 "stream": torch.cuda.Stream()}
+            assert d["stream"].cuda_stream != 0
+            dev.append(d)
 
-    def device_step():
+    def device_step(r):
+        d = dev[r]
         for i in range(0, n_step, cap):
             n = min(cap, n_step - i)
-            model.embed_device(0, d_ids[i:].data_ptr(), d_lens[i:].data_ptr(), n, SEQ, d_out[i:].data_ptr(), stream)
+            model.embed_device(r, d["ids"][i:].data_ptr(), d["lens"][i:].data_ptr(), n, SEQ, d["out"][i:].data_ptr(), d["stream"].cuda_stream)
 
-    with torch.cuda.stream(tstream):
-        for _ in range(args.warmup):
-            device_step()
-    barrier()
+    def device_loop(steps, timed):
+        """`steps` device steps on every replica concurrently; returns the max over replicas of the device time (ms)."""
+        gate = threading.Barrier(N)
+        ms = [0.0] * N
+        errs = []
+
+        def work(r):
+            try:
+                with torch.cuda.device(r):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    gate.wait()
+                    with torch.cuda.stream(dev[r]["stream"]):
+                        e0.record()
+                        for _ in range(steps):
+                            device_step(r)
+                        e1.record()
+                    dev[r]["stream"].synchronize()
+                    ms[r] = e0.elapsed_time(e1)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+                gate.abort()
+
+        th = [threading.Thread(target=work, args=(r,)) for r in range(N)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+        return max(ms)
+
+    def sync_all():
+        for r in range(N):
+            torch.cuda.synchronize(r)
+
+    device_loop(args.warmup, False)
+    sync_all()
     st0 = b200rt.stats()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.25)
     t_wall0 = time.time()
     tw0 = time.perf_counter()
-    with torch.cuda.stream(tstream):
-        e0.record()
-        for _ in range(args.steps):
-            device_step()
-        e1.record()
-    barrier()
+    dev_ms = device_loop(args.steps, True)
+    sync_all()
     tw1 = time.perf_counter()
     t_wall1 = time.time()
-    dev_ms = e0.elapsed_time(e1)
-    assert abs(dev_ms - (tw1 - tw0) * 1e3) < 0.05 * dev_ms + 5.0, "CUDA-event time and synchronised wall time disagree"
+    assert abs(dev_ms - (tw1 - tw0) * 1e3) < 0.05 * dev_ms + 10.0, f"CUDA-event time {dev_ms} and synchronised wall time {(tw1 - tw0) * 1e3} disagree"
     st1 = b200rt.stats()
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1)
     launches = st1["kernel_launches"] - st0["kernel_launches"]
-    tstream.synchronize()
-    norms = torch.linalg.vector_norm(d_out, dim=1)
-    assert torch.allclose(norms, torch.ones_like(norms), atol=1e-3), "device path produced non-unit embeddings"
+    for r in range(N):
+        norms = torch.linalg.vector_norm(dev[r]["out"], dim=1)
+        assert torch.allclose(norms, torch.ones_like(norms), atol=1e-3), "device path produced non-unit embeddings"
 
-    # ---------------- e2e: C ABI with host buffers (.map() inputs of 32 items from pinned memory)
-    n_inputs = n_step // MAP_INPUT_ITEMS
-    pin_ids = b200rt.PinnedBuffer((n_step, SEQ), np.int32)
+    # ---------------- per-kernel device times inside a sustained loop (same warm, power-capped chip as the timed region):
+    # ~1 s of back-to-back forwards with CUDA events between the launches on replica 0's compute stream
+    prof = model.profile_forward(cap, SEQ, iters=60)
+
+    # ---------------- e2e: the C ABI with HOST buffers -- .map() inputs of 32 items lent from pinned memory
+    # (b200rt_submit_ex BORROW_IDS) -> H2D -> scatter kernel -> forward -> fused gather -> D2H into the caller's pinned out
+    n_inputs = n_total // MAP_INPUT_ITEMS
+    pin_ids = b200rt.PinnedBuffer((n_total, SEQ), np.int32)
     pin_ids.array[:] = ids_host
-    pin_out = b200rt.PinnedBuffer((n_step, 768), np.float32)
+    pin_out = b200rt.PinnedBuffer((n_total, 768), np.float32)
 
     def e2e_step():
         tickets = []
         for j in range(n_inputs):
             s = slice(j * MAP_INPUT_ITEMS, (j + 1) * MAP_INPUT_ITEMS)
-            tickets.append(model.submit(pin_ids.array[s], None, out=pin_out.array[s]))
+            tickets.append(model.submit(pin_ids.array[s], None, out=pin_out.array[s], borrow_ids=True))
         for t in tickets:
             model.wait(t)
 
     for _ in range(max(1, args.warmup)):
         e2e_step()
-    barrier()
+    sync_all()
     s0 = b200rt.stats()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
-    barrier()
+    sync_all()
     e2e_s = time.perf_counter() - t0
     s1 = b200rt.stats()
     e2e_out = pin_out.array.copy()
     assert np.allclose(np.linalg.norm(e2e_out, axis=1), 1.0, atol=1e-3)
-    dev_out = d_out.cpu().numpy()
+    dev_out = np.concatenate([dev[r]["out"].cpu().numpy() for r in range(N)])
     assert float(np.abs(dev_out - e2e_out).max()) < 1e-5, "device-resident and host-buffer paths disagree"
 
-    # ---------------- the device-resident loop once more, now on a chip as warm as the e2e loop saw it: separates the
+    # ---------------- the device-resident loop once more, now on chips as warm as the e2e loop saw them: separates the
     # cost of the host path from power-cap clock drift between the two timed regions
-    barrier()
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(tstream):
-        r0.record()
-        for _ in range(args.steps):
-            device_step()
-        r1.record()
-    barrier()
-    dev_ms_after = r0.elapsed_time(r1)
+    dev_ms_after = device_loop(args.steps, True)
+    sync_all()
+
+    # ---------------- e2e_map: the same items through the `modal` shim -- examples/embed_bge_native.py's class,
+    # `model.embed.map(generate_batches(), order_outputs=False)` exactly as text_embeddings_inference.py:167 calls it
+    ex = _load_example()
+    shim_obj = ex.TextEmbeddings(n_gpus=N)
+    data = [(i, ids_host[i]) for i in range(n_total)]
+
+    def batches(items, size):
+        for j in range(0, len(items) - size + 1, size):  # remainder dropped, as the reference does (:156-163)
+            yield items[j:j + size]
+
+    def map_pass(items, size):
+        done = 0
+        t_0 = time.perf_counter()
+        for out_batch in shim_obj.embed.map(batches(items, size), order_outputs=False):
+            done += len(out_batch)
+        return done, time.perf_counter() - t_0
+
+    shim_obj.embed.remote(data[:MAP_INPUT_ITEMS])  # cold start (engine attach + weight upload) outside the timed region
+    map_pass(data, MAP_INPUT_ITEMS)                # warm-up pass
+    map_steps = max(2, args.steps // 4)
+    e2e_map = {"api": "modal shim: TextEmbeddings().embed.map(generate_batches(), order_outputs=False) (examples/embed_bge_native.py)",
+               "unit": "items/s"}
+    for size, key in ((MAP_INPUT_ITEMS, "value"), (1024, "value_1024_per_input")):
+        done, dt = 0, 0.0
+        for _ in range(map_steps):
+            d_, t_ = map_pass(data, size)
+            done += d_
+            dt += t_
+        e2e_map[key] = done / dt
+    big = 65536
+    reps = -(-big // n_total)
+    big_items = (data * reps)[:big]
+    done, dt = map_pass(big_items, MAP_INPUT_ITEMS)
+    e2e_map["pass_65536_items"] = {"items": done, "seconds": dt, "value": done / dt, "map_input_items": MAP_INPUT_ITEMS}
+    e2e_map["steps"] = map_steps
+    st_map = b200rt.stats()
 
     # ---------------- p50 per-item latency: one 512-token item through the same C ABI, host buffers
     one_ids = pin_ids.array[:1]
@@ -321,77 +464,94 @@ def main_ours(args):
     lat = []
     for i in range(1100):  # 1 000 trials after 100 warm-ups
         t1 = time.perf_counter()
-        model.wait(model.submit(one_ids, None, out=one_out))
+        model.wait(model.submit(one_ids, None, out=one_out, borrow_ids=True))
         if i >= 100:
             lat.append((time.perf_counter() - t1) * 1e3)
     lat.sort()
     p50_ms, p99_ms = lat[len(lat) // 2], lat[int(len(lat) * 0.99) - 1]
+    lat_map = []
+    one_item = data[:1]
+    for i in range(300):  # the same through the shim: embed.remote([one item])
+        t1 = time.perf_counter()
+        shim_obj.embed.remote(one_item)
+        if i >= 50:
+            lat_map.append((time.perf_counter() - t1) * 1e3)
+    lat_map.sort()
 
-    # ---------------- max over ranks
-    if use_dist:
-        t = torch.tensor([dev_ms, e2e_s, dev_ms_after], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, dev_ms_after = float(t[0]), float(t[1]), float(t[2])
-        ln = torch.tensor([launches], dtype=torch.int64, device="cuda")
-        dist.all_reduce(ln, op=dist.ReduceOp.SUM)
-        launches = int(ln[0])
-    total_items = args.steps * n_step * world
+    total_items = args.steps * n_total
     value = total_items / (dev_ms / 1e3)
     e2e_value = total_items / e2e_s
 
-    roofline = None
+    # ---------------- roofline of the dominant kernel (device events between launches, compute stream, sustained loop)
+    top = max((k for k in prof if k in KERNEL_FLOPS), key=lambda k: prof[k])
+    n_launch = g.layers
+    achieved = KERNEL_FLOPS[top] * cap * n_launch / (prof[top] / 1e3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(top)
+    total_ms = sum(prof.values())
+    roofline = {
+        "bound": "tensor", "kernel": top, "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["tflops_sustained"], "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16/fp16 dense",
+        "launch_ms": prof[top] / n_launch, "share_of_forward": prof[top] / total_ms,
+        "forward": {"items_per_s_per_gpu": value / N, "tflops": value / N * FLOPS_PER_ITEM / 1e12,
+                    "frac_of_tensor_peak": value / N * FLOPS_PER_ITEM / 1e12 / peaks["tflops_sustained"],
+                    "frac_of_tensor_peak_burst": value / N * FLOPS_PER_ITEM / 1e12 / peaks["tflops_burst"]},
+        "per_kernel_ms": prof, "per_kernel_ms_what": f"sum over {n_launch} layers of one {cap}-item wave, averaged over 60 back-to-back forwards (sustained clocks)",
+        "tensor_kernels": {k: {"TFLOPs": KERNEL_FLOPS[k] * cap * n_launch / (prof[k] / 1e3) / 1e12,
+                               "frac": KERNEL_FLOPS[k] * cap * n_launch / (prof[k] / 1e3) / 1e12 / peaks["tflops_sustained"]}
+                           for k in KERNEL_FLOPS if k in prof},
+        "hbm_kernels": {k: {"GBps": KERNEL_BYTES[k] * cap * SEQ * (n_launch if k != "embed_ln" else 1) / (prof[k] / 1e3) / 1e9,
+                            "frac": KERNEL_BYTES[k] * cap * SEQ * (n_launch if k != "embed_ln" else 1) / (prof[k] / 1e3) / 1e9 / peaks["hbm_gbs"]}
+                        for k in KERNEL_BYTES if k in prof},
+    }
     cpu_baseline = None
-    if rank == 0:
-        # ---------------- roofline of the dominant kernel (device events between launches, compute stream)
-        prof = model.profile_forward(cap, SEQ, iters=3)
-        top = max((k for k in prof if k in KERNEL_FLOPS), key=lambda k: prof[k])
-        n_launch = g.layers
-        achieved = KERNEL_FLOPS[top] * cap * n_launch / (prof[top] / 1e3) / 1e12
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(top)
-        total_ms = sum(prof.values())
-        roofline = {
-            "bound": "tensor", "kernel": top, "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tflops_sustained"], "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16/fp16 dense",
-            "launch_ms": prof[top] / n_launch, "share_of_forward": prof[top] / total_ms,
-            "forward": {"items_per_s_per_gpu": value / world, "tflops": value / world * FLOPS_PER_ITEM / 1e12,
-                        "frac_of_tensor_peak": value / world * FLOPS_PER_ITEM / 1e12 / peaks["tflops_sustained"]},
-            "per_kernel_ms": prof,
-            "hbm_kernels": {k: {"GBps": KERNEL_BYTES[k] * cap * SEQ * (n_launch if k != "embed_ln" else 1) / (prof[k] / 1e3) / 1e9,
-                                "frac": KERNEL_BYTES[k] * cap * SEQ * (n_launch if k != "embed_ln" else 1) / (prof[k] / 1e3) / 1e9 / peaks["hbm_gbs"]}
-                            for k in KERNEL_BYTES if k in prof},
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            v, threads, dt, _, _ = cpu_reference_run(n_items=16, warm_items=4)
-            cpu_baseline = {"value": v, "unit": "items/s", "cores": threads, "kind": "port",
-                            "sample": f"16 items x {SEQ} tokens after a 4-item warm-up ({dt:.1f} s), HF BertModel fp32 (oracle), torch {threads} threads"}
-        line = {
-            "metric": METRIC, "value": value, "unit": "items/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16", "data": "synthetic",
-            "config": {"workload": f"06_gpu_and_ml/embeddings: BGE-base-en-v1.5 embed, synthetic {SEQ}-token items, .map() inputs of {MAP_INPUT_ITEMS}",
-                       "seq_len": SEQ, "items_per_step_per_gpu": n_step, "map_input_items": MAP_INPUT_ITEMS, "device_batch_items": cap,
-                       "weights": "HF default init, numpy default_rng(0), shared with the oracle", "parallelism": f"replicas x{world} (no data-path collective)",
-                       "l2": "per-step working set (218 MB fp16 weights + ~1.3 GB activations) exceeds the 126 MB L2; no explicit flush",
-                       "precision": "fp16 tensor-core operands, fp32 accumulate, fp32 residual/LayerNorm/softmax"},
-            "e2e": {"value": e2e_value, "unit": "items/s", "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"]) // args.steps,
-                    "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"]) // args.steps, "ms_per_step": e2e_s / args.steps * 1e3,
-                    "api": "b200rt_submit/b200rt_wait (C ABI, pinned host buffers)",
-                    "device_resident_rerun_after_e2e": total_items / (dev_ms_after / 1e3),
-                    "per_step_ms": {k: (s1[k] - s0[k]) / args.steps / 1e3 for k in ("stage_us", "h2d_scatter_us", "forward_us", "gap_us", "d2h_us")}},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "latency": {"p50_ms": p50_ms, "p99_ms": p99_ms, "what": "one 512-token item, b200rt_submit+b200rt_wait, pinned host buffers, 1000 trials after 100 warm-ups (rank 0)"},
-        }
-        if cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline
-        GUARD.emit(json.dumps(line))
+    if N == 1 and not args.no_cpu_baseline:
+        v, threads, dt, _, _ = cpu_reference_run(n_items=16, warm_items=4)
+        host_cores = os.cpu_count()
+        try:
+            usable = len(os.sched_getaffinity(0))
+        except Exception:
+            usable = host_cores
+        cpu_baseline = {"value": v, "unit": "items/s", "cores": threads, "host_cores": host_cores, "usable_cores": usable, "kind": "port",
+                        "sample": f"16 items x {SEQ} tokens after a 4-item warm-up ({dt:.1f} s), HF BertModel fp32 (oracle), torch {threads} threads "
+                                  f"(fastest of a sweep; the host shows {host_cores} cores, {usable} usable by this process)"}
+    per_step = lambda a, b_, k, n: (b_[k] - a[k]) / n  # noqa: E731
+    line = {
+        "metric": METRIC, "value": value, "unit": "items/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic",
+        "config": {"workload": f"06_gpu_and_ml/embeddings: BGE-base-en-v1.5 embed, synthetic {SEQ}-token items, .map() inputs of {MAP_INPUT_ITEMS}",
+                   "seq_len": SEQ, "items_per_step_per_gpu": n_step, "items_per_step": n_total, "map_input_items": MAP_INPUT_ITEMS, "device_batch_items": cap,
+                   "weights": "HF default init, numpy default_rng(0), shared with the oracle",
+                   "parallelism": f"ONE process, one pool of {N} replica(s): scatter kernel -> peer HBM, forward per replica, pool+normalise stores into the root's gather buffer (no NCCL on the data path)",
+                   "l2": "per-step working set (218 MB fp16 weights + ~1.3 GB activations per replica) exceeds the 126 MB L2; no explicit flush",
+                   "precision": "fp16 tensor-core operands, fp32 accumulate, fp32 residual/LayerNorm/softmax"},
+        "pool": {"replicas": N, "driving_processes": 1, "peer_bytes_per_step": per_step(s0, s1, "peer_bytes", args.steps),
+                 "waves_per_step": per_step(s0, s1, "waves", args.steps)},
+        "e2e": {"value": e2e_value, "unit": "items/s", "h2d_bytes_per_step": int(per_step(s0, s1, "h2d_bytes", args.steps)),
+                "d2h_bytes_per_step": int(per_step(s0, s1, "d2h_bytes", args.steps)), "peer_bytes_per_step": int(per_step(s0, s1, "peer_bytes", args.steps)),
+                "ms_per_step": e2e_s / args.steps * 1e3,
+                "api": "b200rt_submit_ex(BORROW_IDS)/b200rt_wait (C ABI; ids and out in b200rt_alloc_pinned memory, DMA'd in place)",
+                "device_resident_rerun_after_e2e": total_items / (dev_ms_after / 1e3),
+                "per_step_ms": {k: (s1[k] - s0[k]) / args.steps / 1e3 for k in ("stage_us", "dispatch_us", "h2d_scatter_us", "forward_us", "gap_us", "d2h_us")}},
+        "e2e_map": e2e_map,
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+        "latency": {"p50_ms": p50_ms, "p99_ms": p99_ms, "what": "one 512-token item, b200rt_submit_ex+b200rt_wait, pinned host buffers, 1000 trials after 100 warm-ups",
+                    "shim_remote_p50_ms": lat_map[len(lat_map) // 2], "shim_remote_p99_ms": lat_map[int(len(lat_map) * 0.99) - 1]},
+    }
+    if indep:
+        line["independent_replicas"] = indep
+    if cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline
+    GUARD.emit(json.dumps(line))
     pin_ids.free()
     pin_out.free()
+    shim_obj._teardown()  # runs the class's @modal.exit hook, which shuts the runtime down
     b200rt.shutdown()
+    host_barrier()
     if use_dist:
-        dist.barrier()
         dist.destroy_process_group()
     return 0
 

@@ -24,20 +24,9 @@ with modal.Image.debian_slim().imports():
 
 def random_blob(seed: int = 0):
     """HF-default-init weights (normal sigma 0.02, zero bias, unit LayerNorm) in b200rt's blob order."""
-    rng = np.random.default_rng(seed)
-    g = GEOMETRY
-    h, i = g["hidden"], g["inter"]
-    parts = [rng.standard_normal((g["vocab"] + g["max_pos"] + g["type_vocab"]) * h, dtype=np.float32) * np.float32(0.02),
-             np.ones(h, np.float32), np.zeros(h, np.float32)]
-    for _ in range(g["layers"]):
-        for n_w, n_b in ((3 * h * h, 3 * h), (h * h, h)):
-            parts += [rng.standard_normal(n_w, dtype=np.float32) * np.float32(0.02), np.zeros(n_b, np.float32)]
-            if n_w == h * h:
-                parts += [np.ones(h, np.float32), np.zeros(h, np.float32)]
-        parts += [rng.standard_normal(i * h, dtype=np.float32) * np.float32(0.02), np.zeros(i, np.float32)]
-        parts += [rng.standard_normal(h * i, dtype=np.float32) * np.float32(0.02), np.zeros(h, np.float32), np.ones(h, np.float32),
-                  np.zeros(h, np.float32)]
-    return np.concatenate(parts)
+    from b200rt.weights import random_blob as rb
+
+    return rb(GEOMETRY, seed)
 
 
 @app.cls(gpu="B200:8", max_containers=1)

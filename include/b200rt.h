@@ -5,8 +5,8 @@
  * as used at 06_gpu_and_ml/embeddings/text_embeddings_inference.py:167 (`model.embed.map(...)`), and its
  * arithmetic is an HTTP call into an un-vendored TEI server (`POST /embed`, same file :100).  The entry
  * points below are what a binding for that path replaces; each cites the reference interface it stands
- * in for.  Plain pointers and sizes only; every function is thread-safe; nothing calls back into the
- * caller.  Return 0 on success, a negative B200RT_E_* code on failure (text via b200rt_last_error()).
+ * in for.  Plain pointers and sizes only; every function is thread-safe (forwards on one replica execute one
+ * after the other on the device whichever stream they were enqueued on); nothing calls back into the caller.  Return 0 on success, a negative B200RT_E_* code on failure (text via b200rt_last_error()).
  */
 #ifndef B200RT_H
 #define B200RT_H
@@ -39,12 +39,15 @@ typedef struct b200rt_stats_t {
     uint64_t h2d_bytes, d2h_bytes;      /* through submit()/wait() */
     uint64_t peer_bytes;                /* scatter + fused-gather bytes that crossed NVLink */
     double stage_us, h2d_scatter_us, forward_us, d2h_us; /* summed per-wave stage times (device events; forward = root replica) */
-    double gap_us;                      /* idle time of the root's compute stream between consecutive waves */
+    double gap_us;                      /* idle time of the first participating replica's compute stream between consecutive waves */
+    double dispatch_us;                 /* host time the dispatcher spent forming, staging and enqueueing waves */
 } b200rt_stats_t;
 
 /* Replica pool.  Stands in for `@app.cls(gpu=..., max_containers=N)` + `@modal.concurrent`
  * (text_embeddings_inference.py:79-86): n_gpus local B200s instead of N cloud containers.  Enables peer
  * access between all of them and starts the scheduler threads.  devices = NULL means 0..n_gpus-1.    */
+/* flags: bits 0-15 = items of 512 tokens one replica takes per wave (0 = default 128), see B200RT_INIT_WAVE_ITEMS */
+#define B200RT_INIT_WAVE_ITEMS(n) ((uint32_t)(n) & 0xFFFFu)
 int b200rt_init(int n_gpus, uint32_t flags);
 int b200rt_init_devices(const int* devices, int n_gpus, uint32_t flags);
 int b200rt_num_gpus(void);
@@ -61,7 +64,14 @@ int b200rt_model_load(const char* kind, const void* cfg, const void* weights, si
  * must remain valid until the ticket completes; ids/lens may be reused as soon as submit returns.     */
 int b200rt_submit(int model, const int32_t* ids, const int32_t* lens, int n_items, int max_len, float* out,
                   uint64_t* ticket_out);
-/* Completion, ordered (`order_outputs=True`) ...                                                      */
+/* Zero-copy variant (host wire format).  B200RT_SUBMIT_BORROW_IDS: the caller keeps `ids` valid
+ * and unchanged until the ticket completes, and the library does not take a private copy; when `ids` (at the
+ * wave's padded length) and/or `out` lie inside a b200rt_alloc_pinned() allocation they are DMA'd from / to where
+ * they lie instead of passing through the scheduler's staging buffers.                                          */
+#define B200RT_SUBMIT_BORROW_IDS 1u
+int b200rt_submit_ex(int model, const int32_t* ids, const int32_t* lens, int n_items, int max_len, float* out,
+                     uint32_t flags, uint64_t* ticket_out);
+/* Completion, ordered (`order_outputs=True`): a ticket being waited on is never handed to b200rt_poll_any ...  */
 int b200rt_wait(uint64_t ticket, int timeout_ms); /* timeout_ms < 0: forever */
 /* ... and unordered (`order_outputs=False`, text_embeddings_inference.py:167): next finished ticket
  * that nobody has waited on yet; B200RT_TIMEOUT when none is ready within timeout_ms.                 */

@@ -24,7 +24,7 @@ E_INVALID, E_STATE, E_CUDA, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4, -5
 
 # every symbol include/b200rt.h and include/b200rt_debug.h declare (tests check the export list)
 ABI_SYMBOLS = [
-    "b200rt_init", "b200rt_init_devices", "b200rt_num_gpus", "b200rt_model_load", "b200rt_submit", "b200rt_wait",
+    "b200rt_init", "b200rt_init_devices", "b200rt_num_gpus", "b200rt_model_load", "b200rt_submit", "b200rt_submit_ex", "b200rt_wait",
     "b200rt_poll_any", "b200rt_embed_device", "b200rt_device_sync", "b200rt_wave_capacity_items",
     "b200rt_alloc_pinned", "b200rt_free_pinned", "b200rt_stats", "b200rt_last_error", "b200rt_shutdown",
 ]
@@ -45,7 +45,7 @@ class BertConfig(ctypes.Structure):
 
 class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ("items", "waves", "tickets", "kernel_launches", "h2d_bytes", "d2h_bytes", "peer_bytes")] + [
-        (n, ctypes.c_double) for n in ("stage_us", "h2d_scatter_us", "forward_us", "d2h_us", "gap_us")
+        (n, ctypes.c_double) for n in ("stage_us", "h2d_scatter_us", "forward_us", "d2h_us", "gap_us", "dispatch_us")
     ]
 
     def as_dict(self):
@@ -74,6 +74,8 @@ def load_library():
         lib.b200rt_init_devices.argtypes = [i32p, ctypes.c_int, ctypes.c_uint32]
         lib.b200rt_model_load.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, i32p]
         lib.b200rt_submit.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, u64p]
+        lib.b200rt_submit_ex.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                         ctypes.c_uint32, u64p]
         lib.b200rt_wait.argtypes = [ctypes.c_uint64, ctypes.c_int]
         lib.b200rt_poll_any.argtypes = [u64p, ctypes.c_int]
         lib.b200rt_embed_device.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
@@ -110,12 +112,14 @@ def _ptr(a: np.ndarray):
 _initialised = False
 
 
-def init(n_gpus: int = 1, devices=None, flags: int = 0) -> int:
-    """Start the replica pool on ``devices`` (default ``0..n_gpus-1``).  Idempotent per process."""
+def init(n_gpus: int = 1, devices=None, flags: int = 0, wave_items: int = 0) -> int:
+    """Start the replica pool on ``devices`` (default ``0..n_gpus-1``).  Idempotent per process.
+    ``wave_items``: 512-token items one replica takes per wave (0 = the library default, 128)."""
     global _initialised
     lib = load_library()
     if _initialised:
         return lib.b200rt_num_gpus()
+    flags |= wave_items & 0xFFFF
     if devices is not None:
         arr = (ctypes.c_int32 * len(devices))(*devices)
         _check(lib.b200rt_init_devices(arr, len(devices), flags))
@@ -171,6 +175,42 @@ class Ticket:
     id: int
     out: np.ndarray
     tag: object = None
+    ids: object = None  # keeps a lent (BORROW_IDS) input alive until the ticket completes
+
+
+class TicketError(B200RTError):
+    """A ticket completed with an error; carries the ticket so that the caller can tell which input failed."""
+
+    def __init__(self, code: int, msg: str, ticket: "Ticket | None"):
+        super().__init__(code, msg)
+        self.ticket = ticket
+
+
+# b200rt_poll_any is process-global, so the registry of live tickets is too (not per model): a ticket is registered
+# under the lock that also covers its b200rt_submit call, so a poll_any thread that reaps it early blocks on the lock
+# until the entry exists.
+_live: dict[int, Ticket] = {}
+_live_lock = threading.Lock()
+
+SUBMIT_BORROW_IDS = 1
+
+
+def poll_any(timeout_ms: int = -1) -> Ticket | None:
+    """Next finished ticket nobody is waiting on (any model); None on timeout.  Raises :class:`TicketError` (with the
+    ticket attached) when that ticket failed."""
+    lib = load_library()
+    t = ctypes.c_uint64(0)
+    rc = lib.b200rt_poll_any(ctypes.byref(t), timeout_ms)
+    if rc == TIMEOUT:
+        return None
+    with _live_lock:
+        tk = _live.pop(t.value, None)
+    if rc < 0:
+        msg = (lib.b200rt_last_error() or b"").decode(errors="replace")
+        if t.value == 0:
+            raise B200RTError(rc, msg)
+        raise TicketError(rc, msg, tk)
+    return tk
 
 
 class EmbedModel:
@@ -186,10 +226,12 @@ class EmbedModel:
         _check(lib.b200rt_model_load(b"bert", ctypes.byref(self.cfg), _ptr(blob), blob.nbytes, ctypes.byref(h)))
         self.handle = h.value
         self._lib = lib
-        self._live = {}
-        self._lock = threading.Lock()
 
-    def submit(self, ids: np.ndarray, lens=None, out: np.ndarray | None = None, tag=None) -> Ticket:
+    def submit(self, ids: np.ndarray, lens=None, out: np.ndarray | None = None, tag=None, borrow_ids: bool = False) -> Ticket:
+        """``borrow_ids``: the caller promises not to touch ``ids`` until the ticket completes; the library then takes
+        no private copy and, when ``ids``/``out`` live in :class:`PinnedBuffer` memory, DMAs from/to them directly."""
+        if borrow_ids and not (isinstance(ids, np.ndarray) and ids.dtype == np.int32 and ids.flags.c_contiguous):
+            raise B200RTError(E_INVALID, "borrow_ids needs a C-contiguous int32 array (a converted copy would be freed too early)")
         ids = np.ascontiguousarray(ids, dtype=np.int32)
         if ids.ndim != 2:
             raise B200RTError(E_INVALID, f"ids must be [n_items, max_len], got shape {ids.shape}")
@@ -203,32 +245,32 @@ class EmbedModel:
         elif out.dtype != np.float32 or not out.flags.c_contiguous or out.shape != (n, self.hidden):
             raise B200RTError(E_INVALID, "out must be a C-contiguous float32 [n_items, hidden] array")
         t = ctypes.c_uint64(0)
-        _check(self._lib.b200rt_submit(self.handle, _ptr(ids), _ptr(lens) if lens is not None else None, n, S, _ptr(out),
-                                       ctypes.byref(t)))
-        tk = Ticket(t.value, out, tag)
-        with self._lock:
-            self._live[tk.id] = tk
+        with _live_lock:
+            _check(self._lib.b200rt_submit_ex(self.handle, _ptr(ids), _ptr(lens) if lens is not None else None, n, S, _ptr(out),
+                                              SUBMIT_BORROW_IDS if borrow_ids else 0, ctypes.byref(t)))
+            tk = Ticket(t.value, out, tag, ids if borrow_ids else None)
+            _live[tk.id] = tk
         return tk
 
     def wait(self, ticket: Ticket, timeout_ms: int = -1) -> np.ndarray | None:
-        rc = _check(self._lib.b200rt_wait(ticket.id, timeout_ms))
+        rc = self._lib.b200rt_wait(ticket.id, timeout_ms)
         if rc == TIMEOUT:
             return None
-        with self._lock:
-            self._live.pop(ticket.id, None)
+        with _live_lock:
+            _live.pop(ticket.id, None)
+        if rc < 0:
+            raise TicketError(rc, (self._lib.b200rt_last_error() or b"").decode(errors="replace"), ticket)
         return ticket.out
 
     def poll_any(self, timeout_ms: int = -1) -> Ticket | None:
-        t = ctypes.c_uint64(0)
-        rc = _check(self._lib.b200rt_poll_any(ctypes.byref(t), timeout_ms))
-        if rc == TIMEOUT:
-            return None
-        with self._lock:
-            return self._live.pop(t.value)
+        """Process-wide (see :func:`poll_any`): may return a ticket submitted through another model."""
+        return poll_any(timeout_ms)
 
     def embed(self, ids: np.ndarray, lens=None) -> np.ndarray:
-        """Synchronous convenience: one input in, its embeddings out."""
-        return self.wait(self.submit(ids, lens))
+        """Synchronous convenience: one input in, its embeddings out.  The caller is blocked for the duration, so a
+        C-contiguous int32 ``ids`` is lent to the library instead of copied."""
+        lend = isinstance(ids, np.ndarray) and ids.dtype == np.int32 and ids.flags.c_contiguous
+        return self.wait(self.submit(ids, lens, borrow_ids=lend))
 
     def embed_device(self, gpu: int, d_ids: int, d_lens: int, n_items: int, max_len: int, d_out: int, stream: int = 0):
         """Device-resident forward (raw device addresses); asynchronous on ``stream``."""

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -127,7 +128,8 @@ int make_map_qkv(CUtensorMap* m, const void* base, uint64_t B, uint64_t S, uint6
 
 // ------------------------------------------------------------------------------------------ model / device state
 
-constexpr int NSLOT = 3;
+constexpr int NSLOT = 4;
+constexpr int MIN_ITEMS_PER_REPLICA = 8;  // a wave uses fewer replicas rather than giving one fewer items than this
 constexpr int MAX_SEQ = 512;
 
 struct LayerW {
@@ -163,23 +165,41 @@ struct Dev {
     CUtensorMap m_y32;                    // fp32 [rows,768] box {32,128}: the fp32 epilogues update y32 in place
     std::unordered_map<int, std::pair<CUtensorMap, CUtensorMap>> m_qkv_by_S;  // (qkv, ctx) 3D maps per padded length
     // wave input slots (written by the root's scatter kernel, possibly over NVLink)
-    int32_t* ids_in[NSLOT] = {nullptr, nullptr, nullptr};
-    int32_t* lens_in[NSLOT] = {nullptr, nullptr, nullptr};
+    int32_t* ids_in[NSLOT] = {};
+    int32_t* lens_in[NSLOT] = {};
     cudaEvent_t ev_done[NSLOT];
     cudaEvent_t ev_begin[NSLOT], ev_end[NSLOT];  // timing: the forward itself on this replica's compute stream
     std::mutex mu;  // serialises host-side enqueue on this replica (scheduler vs. embed_device/debug)
+    // Every forward on this replica uses the same workspace (y32, x16, qkv, ctx, ffn, stats), whichever stream it is
+    // enqueued on: ev_ws is recorded behind each forward and waited on ahead of the next one, so forwards from the
+    // scheduler's stream and from callers' streams (b200rt_embed_device) execute one after the other on the device.
+    cudaEvent_t ev_ws = nullptr;
+    bool ev_ws_armed = false;
+    // launcher thread: enqueues this replica's share of a wave (the ~85 launches per replica would otherwise be issued
+    // by the one dispatcher thread for all replicas in turn)
+    std::thread launcher;
+    std::mutex lmu;
+    std::condition_variable lcv;
+    std::function<void()> ltask;
+    bool lstop = false;
 };
 
+struct Model;
 struct Ticket {
     uint64_t id;
     int model;
-    std::vector<int32_t> ids;   // private copy [n, S]
+    const Model* mp = nullptr;  // resolved at submit time (the models vector may grow while the ticket is queued)
+    std::vector<int32_t> ids;   // private copy [n, S] (empty when the caller lent us its buffer: `borrowed`)
+    const int32_t* ids_ext = nullptr;
+    bool borrowed = false, ids_pinned = false, out_pinned = false;
+    const int32_t* ids_ptr() const { return borrowed ? ids_ext : ids.data(); }
     std::vector<int32_t> lens;
     int n_items, S;
     float* out;
     int next_item = 0;          // dispatcher cursor
     std::atomic<int> remaining; // items not yet delivered
-    bool done = false, claimed = false;
+    bool done = false;
+    int waiters = 0;            // threads blocked in b200rt_wait on this ticket: poll_any must not hand it out
     int status = 0;
     std::string error;
 };
@@ -192,6 +212,8 @@ struct Segment {
 struct Wave {
     int slot;
     int n_items, S;
+    int first_dev = 0;        // lowest replica that took part (its events time the forward)
+    bool direct_h2d = false;  // some segments were DMA'd from caller-pinned memory
     std::vector<Segment> segs;
 };
 
@@ -209,17 +231,19 @@ struct Runtime {
     cudaEvent_t ev_scatter[NSLOT], ev_wave[NSLOT], ev_t0[NSLOT], ev_fwd_end[NSLOT];
     // queues
     std::mutex mu;
-    std::condition_variable cv_submit, cv_done, cv_slot, cv_wave;
+    std::condition_variable cv_submit, cv_done, cv_slot, cv_wave, cv_idle;
     std::deque<std::shared_ptr<Ticket>> pending;
     std::unordered_map<uint64_t, std::shared_ptr<Ticket>> tickets;
     std::deque<uint64_t> finished_unclaimed;
     std::deque<Wave> inflight;
-    bool slot_busy[NSLOT] = {false, false, false};
+    bool slot_busy[NSLOT] = {};
+    int fill_window_us = 200;
+    int active_calls = 0;  // threads inside b200rt_wait / b200rt_poll_any (shutdown waits for them to leave)
     uint64_t next_ticket = 1, next_wave = 0;
     bool stopping = false;
     std::thread dispatcher, completer;
     b200rt_stats_t stats{};
-    int last_end_slot = -1;  // completer only
+    int last_end_slot = -1, last_end_dev = -1;  // completer only
     std::mutex stats_mu;
     std::string async_error;
 };
@@ -325,10 +349,15 @@ struct GraphKey {
 struct GraphEntry {
     cudaGraphExec_t exec;
     uint64_t launches;
+    uint64_t last_use;
+};
+struct GraphCache {
+    std::map<GraphKey, GraphEntry> entries;
+    uint64_t tick = 0;
 };
 std::mutex g_graph_mu;
-std::map<Dev*, std::map<GraphKey, GraphEntry>> g_graphs;
-std::map<GraphKey, GraphEntry>& graph_cache(Dev& d) {
+std::map<Dev*, GraphCache> g_graphs;
+GraphCache& graph_cache(Dev& d) {
     std::lock_guard<std::mutex> lk(g_graph_mu);
     return g_graphs[&d];
 }
@@ -336,39 +365,58 @@ void drop_graphs(Dev& d) {  // the replica is going away: its cached launches po
     std::lock_guard<std::mutex> lk(g_graph_mu);
     auto it = g_graphs.find(&d);
     if (it == g_graphs.end()) return;
-    for (auto& kv : it->second) cudaGraphExecDestroy(kv.second.exec);
+    for (auto& kv : it->second.entries) cudaGraphExecDestroy(kv.second.exec);
     g_graphs.erase(it);
 }
 
+// The caller holds d.mu.  Orders this forward behind the previous one on the replica's workspace (see Dev::ev_ws).
 int forward(Dev& d, const Model& m, int dev_index, const int32_t* ids, const int32_t* lens, int B, int S, float* out,
             cudaStream_t stream, int n_layers = -1, Prof* prof = nullptr, uint64_t* launches = nullptr) {
+    if (d.ev_ws_armed) CUDA_TRY(cudaStreamWaitEvent(stream, d.ev_ws, 0));
+    int rc = 0;
+    bool use_graph = !(n_layers >= 0 || prof || B * S > GRAPH_MAX_ROWS);
+#ifdef B200RT_DIAG
     static const bool no_graphs = getenv("B200RT_NO_GRAPHS") != nullptr;
-    if (n_layers >= 0 || prof || B * S > GRAPH_MAX_ROWS || no_graphs)
-        return forward_enqueue(d, m, dev_index, ids, lens, B, S, out, stream, n_layers, prof, launches);
-    auto& cache = graph_cache(d);
-    const GraphKey key{&m, ids, lens, out, stream, B, S};
-    auto it = cache.find(key);
-    if (it == cache.end()) {
-        if (cache.size() >= GRAPH_CACHE_MAX) return forward_enqueue(d, m, dev_index, ids, lens, B, S, out, stream, -1, nullptr, launches);
-        const CUtensorMap *mq = nullptr, *mc = nullptr;
-        if (int rc = get_qkv_map(d, S, &mq, &mc)) return rc;  // host-side map creation happens outside the capture
-        uint64_t nl = 0;
-        CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = forward_enqueue(d, m, dev_index, ids, lens, B, S, out, stream, -1, nullptr, &nl);
-        cudaGraph_t graph = nullptr;
-        const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
-        if (rc) {
-            if (graph) cudaGraphDestroy(graph);
-            return rc;
+    if (no_graphs) use_graph = false;
+#endif
+    if (!use_graph) {
+        rc = forward_enqueue(d, m, dev_index, ids, lens, B, S, out, stream, n_layers, prof, launches);
+    } else {
+        GraphCache& cache = graph_cache(d);
+        const GraphKey key{&m, ids, lens, out, stream, B, S};
+        auto it = cache.entries.find(key);
+        if (it == cache.entries.end()) {
+            if (cache.entries.size() >= GRAPH_CACHE_MAX) {  // evict the least recently replayed graph
+                auto victim = cache.entries.begin();
+                for (auto j = cache.entries.begin(); j != cache.entries.end(); ++j)
+                    if (j->second.last_use < victim->second.last_use) victim = j;
+                cudaGraphExecDestroy(victim->second.exec);
+                cache.entries.erase(victim);
+            }
+            const CUtensorMap *mq = nullptr, *mc = nullptr;
+            if (int r2 = get_qkv_map(d, S, &mq, &mc)) return r2;  // host-side map creation happens outside the capture
+            uint64_t nl = 0;
+            CUDA_TRY(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            rc = forward_enqueue(d, m, dev_index, ids, lens, B, S, out, stream, -1, nullptr, &nl);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(stream, &graph);
+            if (rc) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            CUDA_TRY(ce);
+            GraphEntry ent{nullptr, nl, 0};
+            CUDA_TRY(cudaGraphInstantiate(&ent.exec, graph, 0));
+            cudaGraphDestroy(graph);
+            it = cache.entries.emplace(key, ent).first;
         }
-        CUDA_TRY(ce);
-        GraphEntry ent{nullptr, nl};
-        CUDA_TRY(cudaGraphInstantiate(&ent.exec, graph, 0));
-        cudaGraphDestroy(graph);
-        it = cache.emplace(key, ent).first;
+        it->second.last_use = ++cache.tick;
+        CUDA_TRY(cudaGraphLaunch(it->second.exec, stream));
+        if (launches) *launches += it->second.launches;
     }
-    CUDA_TRY(cudaGraphLaunch(it->second.exec, stream));
-    if (launches) *launches += it->second.launches;
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(d.ev_ws, stream));
+    d.ev_ws_armed = true;
     return 0;
 }
 
@@ -379,7 +427,7 @@ void finish_ticket_locked(Runtime& rt, const std::shared_ptr<Ticket>& t, int sta
     t->done = true;
     t->status = status;
     t->error = err;
-    rt.finished_unclaimed.push_back(t->id);
+    if (t->waiters == 0) rt.finished_unclaimed.push_back(t->id);  // a blocked b200rt_wait owns the ticket otherwise
     rt.stats.tickets++;
 }
 
@@ -401,10 +449,44 @@ void fail_all(Runtime& rt, const std::string& err) {
         }                                                                                            \
     } while (0)
 
+// Pinned allocations handed out by b200rt_alloc_pinned: buffers inside one are DMA targets/sources as they are
+// (no staging copy through the scheduler's own pinned slots).
+std::mutex g_pin_mu;
+std::map<uintptr_t, size_t> g_pinned;  // base -> bytes
+bool is_pinned(const void* p, size_t nbytes) {
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    auto it = g_pinned.upper_bound(a);
+    if (it == g_pinned.begin()) return false;
+    --it;
+    return a >= it->first && a + nbytes <= it->first + it->second;
+}
+
+// Padded lengths are bucketed to multiples of 64 tokens (the attention kernel's key sub-block): tickets whose max_len
+// falls into the same bucket share a wave, padded to the bucket size (at most 63 wasted tokens per item).
+inline int bucket_of(int S) { return std::min(MAX_SEQ, (S + 63) / 64 * 64); }
+
+void launcher_main(Dev* dp) {
+    Dev& d = *dp;
+    cudaSetDevice(d.id);
+    for (;;) {
+        std::function<void()> task;
+        {
+            std::unique_lock<std::mutex> lk(d.lmu);
+            d.lcv.wait(lk, [&] { return d.lstop || d.ltask; });
+            if (d.lstop && !d.ltask) return;
+            task = std::move(d.ltask);
+            d.ltask = nullptr;
+        }
+        task();
+    }
+}
+
 void dispatcher_main(Runtime* rtp) {
     Runtime& rt = *rtp;
     const int G = static_cast<int>(rt.devs.size());
     Dev& root = *rt.devs[0];
+    int rr = 0;  // first replica of the next wave that does not need the whole pool (whole inputs round-robin)
     for (;;) {
         Wave wv;
         {
@@ -416,17 +498,36 @@ void dispatcher_main(Runtime* rtp) {
             rt.cv_slot.wait(lk, [&] { return rt.stopping || !rt.slot_busy[slot]; });
             if (rt.stopping) return;
             if (rt.pending.empty()) continue;
+            // Fill window: while earlier waves keep the GPUs busy, give a partial wave up to FILL_WINDOW_US to grow
+            // (an idle pool dispatches at once: that is the latency path).
+            {
+                const int S0 = bucket_of(rt.pending.front()->S);
+                const int cap0 = (rt.cap_rows / S0) * G;
+                auto queued = [&] {
+                    int n = 0;
+                    for (auto& t : rt.pending) n += t->n_items - t->next_item;
+                    return n;
+                };
+                bool busy = false;
+                for (int s2 = 0; s2 < NSLOT; ++s2) busy |= rt.slot_busy[s2];
+                if (busy && queued() < cap0) {
+                    const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(rt.fill_window_us);
+                    rt.cv_submit.wait_until(lk, deadline, [&] { return rt.stopping || queued() >= cap0; });
+                    if (rt.stopping) return;
+                    if (rt.pending.empty()) continue;
+                }
+            }
             rt.slot_busy[slot] = true;
             rt.next_wave++;
             wv.slot = slot;
-            wv.S = rt.pending.front()->S;
+            wv.S = bucket_of(rt.pending.front()->S);
             wv.n_items = 0;
-            const int model = rt.pending.front()->model;
+            const Model* model = rt.pending.front()->mp;
             // token capacity scales with 512/S: a wave holds cap_rows tokens per replica
             const int cap_items_S = (rt.cap_rows / wv.S) * G;
             while (!rt.pending.empty() && wv.n_items < cap_items_S) {
                 auto t = rt.pending.front();
-                if (t->S != wv.S || t->model != model) break;
+                if (bucket_of(t->S) != wv.S || t->mp != model) break;
                 const int take = std::min(t->n_items - t->next_item, cap_items_S - wv.n_items);
                 wv.segs.push_back(Segment{t, t->next_item, take, wv.n_items});
                 t->next_item += take;
@@ -435,69 +536,163 @@ void dispatcher_main(Runtime* rtp) {
             }
         }
         const int slot = wv.slot, S = wv.S, n = wv.n_items;
-        const Model& model = *rt.models[wv.segs[0].t->model];
+        const Model& model = *wv.segs[0].t->mp;
         auto t_host0 = std::chrono::steady_clock::now();
-        // stage into pinned memory
-        for (const Segment& sg : wv.segs) {
-            memcpy(rt.h_ids[slot] + static_cast<size_t>(sg.wave_off) * S,
-                   sg.t->ids.data() + static_cast<size_t>(sg.ticket_off) * S, static_cast<size_t>(sg.count) * S * 4);
-            memcpy(rt.h_lens[slot] + sg.wave_off, sg.t->lens.data() + sg.ticket_off, static_cast<size_t>(sg.count) * 4);
-        }
-        auto t_host1 = std::chrono::steady_clock::now();
         SCHED_TRY(cudaSetDevice(root.id));
         SCHED_TRY(cudaEventRecord(rt.ev_t0[slot], rt.s_in));
-        SCHED_TRY(cudaMemcpyAsync(rt.d_ids_stage[slot], rt.h_ids[slot], static_cast<size_t>(n) * S * 4,
-                                  cudaMemcpyHostToDevice, rt.s_in));
+        // Stage the wave's ids on the root GPU.  A segment whose ids the caller lent us in pinned memory, at the
+        // wave's own padded length, is DMA'd from where it lies; anything else goes through the slot's pinned buffer
+        // (re-strided to the bucket length when the ticket's max_len is shorter).
+        bool staged = false;
+        for (const Segment& sg : wv.segs) {
+            const Ticket& t = *sg.t;
+            const int32_t* src = t.ids_ptr() + static_cast<size_t>(sg.ticket_off) * t.S;
+            int32_t* hdst = rt.h_ids[slot] + static_cast<size_t>(sg.wave_off) * S;
+            if (t.borrowed && t.S == S && t.ids_pinned) {
+                SCHED_TRY(cudaMemcpyAsync(rt.d_ids_stage[slot] + static_cast<size_t>(sg.wave_off) * S, src,
+                                          static_cast<size_t>(sg.count) * S * 4, cudaMemcpyHostToDevice, rt.s_in));
+                wv.direct_h2d = true;
+                // keep the pinned mirror coherent for the bulk copy below (cheap: it is skipped when every segment is direct)
+                continue;
+            }
+            staged = true;
+            if (t.S == S) {
+                memcpy(hdst, src, static_cast<size_t>(sg.count) * S * 4);
+            } else {
+                for (int i = 0; i < sg.count; ++i) {
+                    memcpy(hdst + static_cast<size_t>(i) * S, src + static_cast<size_t>(i) * t.S, static_cast<size_t>(t.S) * 4);
+                    memset(hdst + static_cast<size_t>(i) * S + t.S, 0, static_cast<size_t>(S - t.S) * 4);
+                }
+            }
+        }
+        for (const Segment& sg : wv.segs)
+            memcpy(rt.h_lens[slot] + sg.wave_off, sg.t->lens.data() + sg.ticket_off, static_cast<size_t>(sg.count) * 4);
+        auto t_host1 = std::chrono::steady_clock::now();
+        if (staged) {
+            if (!wv.direct_h2d) {
+                SCHED_TRY(cudaMemcpyAsync(rt.d_ids_stage[slot], rt.h_ids[slot], static_cast<size_t>(n) * S * 4,
+                                          cudaMemcpyHostToDevice, rt.s_in));
+            } else {  // mixed wave: only the staged segments come from the slot buffer
+                for (const Segment& sg : wv.segs) {
+                    const Ticket& t = *sg.t;
+                    if (t.borrowed && t.S == S && t.ids_pinned) continue;
+                    SCHED_TRY(cudaMemcpyAsync(rt.d_ids_stage[slot] + static_cast<size_t>(sg.wave_off) * S,
+                                              rt.h_ids[slot] + static_cast<size_t>(sg.wave_off) * S,
+                                              static_cast<size_t>(sg.count) * S * 4, cudaMemcpyHostToDevice, rt.s_in));
+                }
+            }
+        }
         SCHED_TRY(cudaMemcpyAsync(rt.d_lens_stage[slot], rt.h_lens[slot], static_cast<size_t>(n) * 4,
                                   cudaMemcpyHostToDevice, rt.s_in));
-        // contiguous item ranges, as even as possible
+        // Replicas used by this wave: everyone when there is enough work, otherwise as many as get at least
+        // MIN_ITEMS_PER_REPLICA items each, starting from a rotating replica so that consecutive small waves land on
+        // different GPUs.  Contiguous item ranges, as even as possible.
         ScatterPlan plan{};
         plan.n_shards = G;
         plan.S = S;
-        const int per = (n + G - 1) / G;
+        int used = std::min(G, std::max(1, n / MIN_ITEMS_PER_REPLICA));
+        const int first = used == G ? 0 : rr;
+        if (used != G) rr = (rr + used) % G;
+        const int per = (n + used - 1) / used;
         uint64_t peer_bytes = 0;
         for (int g = 0; g < G; ++g) {
-            const int b0 = std::min(n, g * per), b1 = std::min(n, (g + 1) * per);
             plan.dst_ids[g] = rt.devs[g]->ids_in[slot];
             plan.dst_lens[g] = rt.devs[g]->lens_in[slot];
+            plan.item_begin[g] = 0;
+            plan.item_count[g] = 0;
+        }
+        for (int k = 0; k < used; ++k) {
+            const int g = (first + k) % G;
+            const int b0 = std::min(n, k * per), b1 = std::min(n, (k + 1) * per);
             plan.item_begin[g] = b0;
             plan.item_count[g] = b1 - b0;
             if (g != 0) peer_bytes += static_cast<uint64_t>(b1 - b0) * (S * 4 + 4 + HIDDEN * 4);
         }
         SCHED_TRY(launch_scatter(rt.d_ids_stage[slot], rt.d_lens_stage[slot], plan, rt.s_in));
         SCHED_TRY(cudaEventRecord(rt.ev_scatter[slot], rt.s_in));
-        uint64_t launches = 1;
+        // every participating replica's launcher thread enqueues its own forward (~85 launches each, in parallel)
+        std::atomic<uint64_t> launches{1};
+        std::atomic<int> left{0};
+        std::mutex jm;
+        std::condition_variable jcv;
+        std::string err;
+        int err_code = 0;
+        for (int g = 0; g < G; ++g)
+            if (plan.item_count[g] > 0) left.fetch_add(1);
+        wv.first_dev = -1;
         for (int g = 0; g < G; ++g) {
             if (plan.item_count[g] == 0) continue;
+            if (wv.first_dev < 0) wv.first_dev = g;
             Dev& d = *rt.devs[g];
-            std::lock_guard<std::mutex> dl(d.mu);
-            SCHED_TRY(cudaSetDevice(d.id));
-            SCHED_TRY(cudaStreamWaitEvent(d.compute, rt.ev_scatter[slot], 0));
-            SCHED_TRY(cudaEventRecord(d.ev_begin[slot], d.compute));
-            float* dst = rt.d_out_gather[slot] + static_cast<size_t>(plan.item_begin[g]) * HIDDEN;
-            int rc = forward(d, model, g, d.ids_in[slot], d.lens_in[slot], plan.item_count[g], S, dst, d.compute, -1,
-                             nullptr, &launches);
-            if (rc) {
-                fail_all(rt, t_last_error);
-                return;
+            auto task = [&, g]() {
+                Dev& dd = *rt.devs[g];
+                std::string e;
+                int code = 0;
+                auto ck = [&](cudaError_t ce, const char* what) {
+                    if (ce != cudaSuccess && e.empty()) { e = std::string(what) + ": " + cudaGetErrorString(ce); code = B200RT_E_CUDA; }
+                    return ce == cudaSuccess;
+                };
+                {
+                    std::lock_guard<std::mutex> dl(dd.mu);
+                    uint64_t nl = 0;
+                    float* dst = rt.d_out_gather[slot] + static_cast<size_t>(plan.item_begin[g]) * HIDDEN;
+                    if (ck(cudaStreamWaitEvent(dd.compute, rt.ev_scatter[slot], 0), "cudaStreamWaitEvent") &&
+                        ck(cudaEventRecord(dd.ev_begin[slot], dd.compute), "cudaEventRecord")) {
+                        int rc = forward(dd, model, g, dd.ids_in[slot], dd.lens_in[slot], plan.item_count[g], S, dst, dd.compute, -1, nullptr, &nl);
+                        if (rc) { e = t_last_error; code = rc; }
+                        else {
+                            ck(cudaEventRecord(dd.ev_end[slot], dd.compute), "cudaEventRecord");
+                            ck(cudaEventRecord(dd.ev_done[slot], dd.compute), "cudaEventRecord");
+                        }
+                    }
+                    launches.fetch_add(nl);
+                }
+                std::lock_guard<std::mutex> jl(jm);
+                if (!e.empty() && err.empty()) { err = e; err_code = code; }
+                left.fetch_sub(1);
+                jcv.notify_one();
+            };
+            if (used == 1 && g == 0) {
+                task();  // the root's own share of a one-replica wave: no hand-off (latency path)
+            } else {
+                std::lock_guard<std::mutex> ll(d.lmu);
+                d.ltask = task;
+                d.lcv.notify_one();
             }
-            SCHED_TRY(cudaEventRecord(d.ev_end[slot], d.compute));
-            SCHED_TRY(cudaEventRecord(d.ev_done[slot], d.compute));
+        }
+        {
+            std::unique_lock<std::mutex> jl(jm);
+            jcv.wait(jl, [&] { return left.load() == 0; });
+        }
+        if (!err.empty()) {
+            if (err_code == B200RT_E_CUDA) g_poisoned.store(true);
+            fail_all(rt, err);
+            return;
         }
         SCHED_TRY(cudaSetDevice(root.id));
         for (int g = 0; g < G; ++g)
             if (plan.item_count[g] > 0) SCHED_TRY(cudaStreamWaitEvent(rt.s_out, rt.devs[g]->ev_done[slot], 0));
         SCHED_TRY(cudaEventRecord(rt.ev_fwd_end[slot], rt.s_out));
-        SCHED_TRY(cudaMemcpyAsync(rt.h_out[slot], rt.d_out_gather[slot], static_cast<size_t>(n) * HIDDEN * 4,
-                                  cudaMemcpyDeviceToHost, rt.s_out));
+        // D2H: rows of a ticket whose `out` lies in pinned memory go straight there; the rest through the slot buffer
+        bool any_staged_out = false;
+        for (const Segment& sg : wv.segs) {
+            if (!sg.t->out_pinned) { any_staged_out = true; continue; }
+            SCHED_TRY(cudaMemcpyAsync(sg.t->out + static_cast<size_t>(sg.ticket_off) * HIDDEN,
+                                      rt.d_out_gather[slot] + static_cast<size_t>(sg.wave_off) * HIDDEN,
+                                      static_cast<size_t>(sg.count) * HIDDEN * 4, cudaMemcpyDeviceToHost, rt.s_out));
+        }
+        if (any_staged_out)
+            SCHED_TRY(cudaMemcpyAsync(rt.h_out[slot], rt.d_out_gather[slot], static_cast<size_t>(n) * HIDDEN * 4,
+                                      cudaMemcpyDeviceToHost, rt.s_out));
         SCHED_TRY(cudaEventRecord(rt.ev_wave[slot], rt.s_out));
         {
             std::lock_guard<std::mutex> sl(rt.stats_mu);
-            rt.stats.kernel_launches += launches;
+            rt.stats.kernel_launches += launches.load();
             rt.stats.h2d_bytes += static_cast<uint64_t>(n) * (S * 4 + 4);
             rt.stats.d2h_bytes += static_cast<uint64_t>(n) * HIDDEN * 4;
             rt.stats.peer_bytes += peer_bytes;
             rt.stats.stage_us += std::chrono::duration<double, std::micro>(t_host1 - t_host0).count();
+            rt.stats.dispatch_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_host0).count();
         }
         {
             std::lock_guard<std::mutex> lk(rt.mu);
@@ -529,19 +724,31 @@ void completer_main(Runtime* rtp) {
             fail_all(rt, std::string("wave failed: ") + cudaGetErrorString(e));
             return;
         }
+        Dev& fd = *rt.devs[wv.first_dev < 0 ? 0 : wv.first_dev];
         float ms_in = 0, ms_fwd = 0, ms_out = 0;
         cudaEventElapsedTime(&ms_in, rt.ev_t0[slot], rt.ev_scatter[slot]);
-        cudaEventElapsedTime(&ms_fwd, rt.devs[0]->ev_begin[slot], rt.devs[0]->ev_end[slot]);  // root replica's forward
+        if (cudaEventElapsedTime(&ms_fwd, fd.ev_begin[slot], fd.ev_end[slot]) != cudaSuccess) { ms_fwd = 0; cudaGetLastError(); }
         float ms_gap = 0;
-        if (rt.last_end_slot >= 0 && cudaEventElapsedTime(&ms_gap, rt.devs[0]->ev_end[rt.last_end_slot], rt.devs[0]->ev_begin[slot]) != cudaSuccess) {
+        if (rt.last_end_slot >= 0 && rt.last_end_dev == wv.first_dev &&
+            cudaEventElapsedTime(&ms_gap, fd.ev_end[rt.last_end_slot], fd.ev_begin[slot]) != cudaSuccess) {
             ms_gap = 0;
             cudaGetLastError();
         }
         rt.last_end_slot = slot;
+        rt.last_end_dev = wv.first_dev;
         cudaEventElapsedTime(&ms_out, rt.ev_fwd_end[slot], rt.ev_wave[slot]);
-        for (const Segment& sg : wv.segs)
-            memcpy(sg.t->out + static_cast<size_t>(sg.ticket_off) * HIDDEN,
-                   rt.h_out[slot] + static_cast<size_t>(sg.wave_off) * HIDDEN, static_cast<size_t>(sg.count) * HIDDEN * 4);
+        {
+            // rows of tickets that already failed or were shut down are not delivered: their owners may have freed `out`
+            std::vector<const Segment*> live;
+            {
+                std::lock_guard<std::mutex> lk(rt.mu);
+                for (const Segment& sg : wv.segs)
+                    if (!sg.t->done && !sg.t->out_pinned) live.push_back(&sg);
+            }
+            for (const Segment* sg : live)
+                memcpy(sg->t->out + static_cast<size_t>(sg->ticket_off) * HIDDEN,
+                       rt.h_out[slot] + static_cast<size_t>(sg->wave_off) * HIDDEN, static_cast<size_t>(sg->count) * HIDDEN * 4);
+        }
         {
             std::lock_guard<std::mutex> sl(rt.stats_mu);
             rt.stats.items += wv.n_items;
@@ -574,6 +781,7 @@ int alloc_dev(Runtime& rt, Dev& d) {
     d.sm_count = prop.multiProcessorCount;
     CUDA_TRY(kernels_init_device());
     CUDA_TRY(cudaStreamCreateWithFlags(&d.compute, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&d.ev_ws, cudaEventDisableTiming));
     const size_t R = rt.cap_rows;
     CUDA_TRY(cudaMalloc(&d.stats, R * sizeof(float2)));
     CUDA_TRY(cudaMemset(d.stats, 0, R * sizeof(float2)));
@@ -605,7 +813,6 @@ int alloc_dev(Runtime& rt, Dev& d) {
 }
 
 int rt_init(const int* devices, int n, uint32_t flags) {
-    (void)flags;
     std::lock_guard<std::mutex> lk(g_rt_mu);
     if (g_rt) return fail(B200RT_E_STATE, "b200rt already initialised");
     if (g_poisoned.load()) return fail(B200RT_E_CUDA, "context poisoned by an earlier CUDA error");
@@ -615,7 +822,8 @@ int rt_init(const int* devices, int n, uint32_t flags) {
     if (e != cudaSuccess || count == 0)
         return fail(B200RT_E_CUDA, "no CUDA device available (%s); b200rt has no CPU path", cudaGetErrorString(e));
     auto rt = std::make_unique<Runtime>();
-    if (const char* s = getenv("B200RT_WAVE_ITEMS")) rt->cap_items = std::max(1, atoi(s));
+    if (flags & 0xFFFFu) rt->cap_items = static_cast<int>(flags & 0xFFFFu);  // B200RT_INIT_WAVE_ITEMS(n)
+    if (rt->cap_items > 1024) return fail(B200RT_E_INVALID, "wave capacity of %d items per replica is out of range (1..1024)", rt->cap_items);
     rt->cap_rows = ((rt->cap_items * MAX_SEQ + 255) / 256) * 256;
     g_rt = rt.get();  // forward() and friends read capacity through g_rt
     auto bail = [&](int rc) { g_rt = nullptr; return rc; };
@@ -661,6 +869,7 @@ int rt_init(const int* devices, int n, uint32_t flags) {
         cudaSetDevice(d->id);
         if (int rc = ck(cudaDeviceSynchronize(), "device sync after init")) return bail(rc);
     }
+    for (auto& d : rt->devs) d->launcher = std::thread(launcher_main, d.get());
     rt->dispatcher = std::thread(dispatcher_main, rt.get());
     rt->completer = std::thread(completer_main, rt.get());
     g_rt = rt.release();
@@ -829,21 +1038,31 @@ int b200rt_model_load(const char* kind, const void* cfg, const void* weights, si
     return model_load(*static_cast<const b200rt_bert_config*>(cfg), static_cast<const float*>(weights), nbytes, model_out);
 }
 
-int b200rt_submit(int model, const int32_t* ids, const int32_t* lens, int n_items, int max_len, float* out,
-                  uint64_t* ticket_out) {
+static int submit_impl(int model, const int32_t* ids, const int32_t* lens, int n_items, int max_len, float* out,
+                       uint32_t flags, uint64_t* ticket_out) {
     Runtime* rt = live_rt();
     if (!rt) return g_poisoned.load() ? B200RT_E_CUDA : B200RT_E_STATE;
     const Model* m = get_model(*rt, model);
     if (!m) return B200RT_E_INVALID;
     if (!out || !ticket_out) return fail(B200RT_E_INVALID, "null out / ticket_out");
+    if (flags & ~static_cast<uint32_t>(B200RT_SUBMIT_BORROW_IDS)) return fail(B200RT_E_INVALID, "unknown submit flags 0x%x", flags);
     if (int rc = check_ids(m->cfg, ids, lens, n_items, max_len)) return rc;
     auto t = std::make_shared<Ticket>();
     t->model = model;
+    t->mp = m;
     t->n_items = n_items;
     t->S = max_len;
     t->out = out;
     t->remaining.store(n_items);
-    t->ids.assign(ids, ids + static_cast<size_t>(n_items) * max_len);
+    const size_t id_bytes = static_cast<size_t>(n_items) * max_len * 4;
+    if (flags & B200RT_SUBMIT_BORROW_IDS) {  // the caller keeps ids valid and unchanged until the ticket completes
+        t->borrowed = true;
+        t->ids_ext = ids;
+        t->ids_pinned = is_pinned(ids, id_bytes);
+    } else {
+        t->ids.assign(ids, ids + static_cast<size_t>(n_items) * max_len);
+    }
+    t->out_pinned = is_pinned(out, static_cast<size_t>(n_items) * HIDDEN * 4);
     if (lens) t->lens.assign(lens, lens + n_items);
     else t->lens.assign(n_items, max_len);
     {
@@ -858,6 +1077,16 @@ int b200rt_submit(int model, const int32_t* ids, const int32_t* lens, int n_item
     return 0;
 }
 
+int b200rt_submit(int model, const int32_t* ids, const int32_t* lens, int n_items, int max_len, float* out,
+                  uint64_t* ticket_out) {
+    return submit_impl(model, ids, lens, n_items, max_len, out, 0, ticket_out);
+}
+
+int b200rt_submit_ex(int model, const int32_t* ids, const int32_t* lens, int n_items, int max_len, float* out,
+                     uint32_t flags, uint64_t* ticket_out) {
+    return submit_impl(model, ids, lens, n_items, max_len, out, flags, ticket_out);
+}
+
 static int reap_locked(Runtime& rt, uint64_t id, const std::shared_ptr<Ticket>& t) {
     for (auto it = rt.finished_unclaimed.begin(); it != rt.finished_unclaimed.end(); ++it)
         if (*it == id) { rt.finished_unclaimed.erase(it); break; }
@@ -866,27 +1095,66 @@ static int reap_locked(Runtime& rt, uint64_t id, const std::shared_ptr<Ticket>& 
     return 0;
 }
 
+// Entry/exit bookkeeping of the blocking calls: b200rt_shutdown waits until nobody is inside before it frees the
+// runtime (callers are woken with "runtime shut down" first).
+struct CallGuard {
+    Runtime* rt = nullptr;
+    std::unique_lock<std::mutex> lk;
+    CallGuard() {
+        std::lock_guard<std::mutex> g(g_rt_mu);
+        rt = g_rt;
+        if (rt) {
+            lk = std::unique_lock<std::mutex>(rt->mu);
+            rt->active_calls++;
+        }
+    }
+    ~CallGuard() {
+        if (rt) {
+            if (!lk.owns_lock()) lk.lock();
+            rt->active_calls--;
+            rt->cv_idle.notify_all();
+            lk.unlock();  // the last access to *rt: b200rt_shutdown may free it as soon as the count reaches zero
+            lk.release();
+        }
+    }
+};
+
 int b200rt_wait(uint64_t ticket, int timeout_ms) {
-    Runtime* rt = g_rt;
+    CallGuard g;
+    Runtime* rt = g.rt;
     if (!rt) return fail(B200RT_E_STATE, "b200rt_init has not been called");
-    std::unique_lock<std::mutex> lk(rt->mu);
+    auto& lk = g.lk;
     auto it = rt->tickets.find(ticket);
     if (it == rt->tickets.end()) return fail(B200RT_E_INVALID, "unknown or already reaped ticket %llu", (unsigned long long)ticket);
     std::shared_ptr<Ticket> t = it->second;
+    // from here on the ticket belongs to this waiter: poll_any will not hand it out
+    t->waiters++;
+    for (auto f = rt->finished_unclaimed.begin(); f != rt->finished_unclaimed.end(); ++f)
+        if (*f == ticket) { rt->finished_unclaimed.erase(f); break; }
     auto pred = [&] { return t->done; };
+    bool ok = true;
     if (timeout_ms < 0) rt->cv_done.wait(lk, pred);
-    else if (!rt->cv_done.wait_for(lk, std::chrono::milliseconds(timeout_ms), pred)) return B200RT_TIMEOUT;
+    else ok = rt->cv_done.wait_for(lk, std::chrono::milliseconds(timeout_ms), pred);
+    t->waiters--;
+    if (rt->tickets.find(ticket) == rt->tickets.end())  // a second waiter on the same ticket lost the race
+        return fail(B200RT_E_INVALID, "ticket %llu was reaped by another waiter", (unsigned long long)ticket);
+    if (!ok) {
+        if (t->done && t->waiters == 0) rt->finished_unclaimed.push_back(ticket);  // (cannot happen: done => ok)
+        return B200RT_TIMEOUT;
+    }
     return reap_locked(*rt, ticket, t);
 }
 
 int b200rt_poll_any(uint64_t* ticket_out, int timeout_ms) {
-    Runtime* rt = g_rt;
-    if (!rt) return fail(B200RT_E_STATE, "b200rt_init has not been called");
     if (!ticket_out) return fail(B200RT_E_INVALID, "null ticket_out");
-    std::unique_lock<std::mutex> lk(rt->mu);
-    auto pred = [&] { return !rt->finished_unclaimed.empty(); };
+    CallGuard g;
+    Runtime* rt = g.rt;
+    if (!rt) return fail(B200RT_E_STATE, "b200rt_init has not been called");
+    auto& lk = g.lk;
+    auto pred = [&] { return !rt->finished_unclaimed.empty() || rt->stopping; };
     if (timeout_ms < 0) rt->cv_done.wait(lk, pred);
     else if (!rt->cv_done.wait_for(lk, std::chrono::milliseconds(timeout_ms), pred)) return B200RT_TIMEOUT;
+    if (rt->finished_unclaimed.empty()) return fail(B200RT_E_STATE, "runtime shut down");
     const uint64_t id = rt->finished_unclaimed.front();
     auto t = rt->tickets[id];
     *ticket_out = id;
@@ -928,10 +1196,19 @@ void* b200rt_alloc_pinned(size_t nbytes) {
         fail(B200RT_E_NOMEM, "cudaMallocHost(%zu) failed", nbytes);
         return nullptr;
     }
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        g_pinned[reinterpret_cast<uintptr_t>(p)] = nbytes;
+    }
     return p;
 }
 void b200rt_free_pinned(void* p) {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        g_pinned.erase(reinterpret_cast<uintptr_t>(p));
+    }
+    cudaFreeHost(p);
 }
 
 int b200rt_stats(b200rt_stats_t* out) {
@@ -952,14 +1229,30 @@ void b200rt_shutdown(void) {
     {
         std::lock_guard<std::mutex> lk(rt->mu);
         rt->stopping = true;
-        for (auto& kv : rt->tickets) finish_ticket_locked(*rt, kv.second, B200RT_E_STATE, "runtime shut down");
     }
+    // 1. no new waves: the dispatcher leaves at its next wait; 2. the completer drains the waves already in flight
+    // (their rows still go to live tickets' buffers) and leaves; 3. only then are the remaining tickets failed and
+    // their waiters woken, so nothing writes a caller's `out` after that caller was told the runtime is gone.
     rt->cv_submit.notify_all();
     rt->cv_slot.notify_all();
-    rt->cv_wave.notify_all();
-    rt->cv_done.notify_all();
     if (rt->dispatcher.joinable()) rt->dispatcher.join();
+    rt->cv_wave.notify_all();
     if (rt->completer.joinable()) rt->completer.join();
+    {
+        std::unique_lock<std::mutex> lk(rt->mu);
+        for (auto& kv : rt->tickets) finish_ticket_locked(*rt, kv.second, B200RT_E_STATE, "runtime shut down");
+        rt->pending.clear();
+        rt->cv_done.notify_all();
+        rt->cv_idle.wait(lk, [&] { return rt->active_calls == 0; });  // blocked b200rt_wait / poll_any callers have left
+    }
+    for (auto& d : rt->devs) {
+        {
+            std::lock_guard<std::mutex> ll(d->lmu);
+            d->lstop = true;
+        }
+        d->lcv.notify_all();
+        if (d->launcher.joinable()) d->launcher.join();
+    }
     for (auto& d : rt->devs) {
         cudaSetDevice(d->id);
         cudaDeviceSynchronize();
@@ -975,6 +1268,7 @@ void b200rt_shutdown(void) {
         drop_graphs(*d);
         cudaFree(d->x32_dbg); cudaFree(d->stats); cudaFree(d->y32); cudaFree(d->x16); cudaFree(d->qkv); cudaFree(d->ctx); cudaFree(d->ffn);
         for (int s = 0; s < NSLOT; ++s) { cudaFree(d->ids_in[s]); cudaFree(d->lens_in[s]); cudaEventDestroy(d->ev_done[s]); cudaEventDestroy(d->ev_begin[s]); cudaEventDestroy(d->ev_end[s]); }
+        cudaEventDestroy(d->ev_ws);
         cudaStreamDestroy(d->compute);
     }
     cudaSetDevice(rt->devs[0]->id);

@@ -88,8 +88,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     const int num_n = N / BN;
     const int num_tiles = num_m * num_n;
     const int kblocks = K / BK;
-    const int nstages = (dbg_mode >> 4) ? (dbg_mode >> 4) : STAGES;  // diagnostics may use a shorter ring
+#ifdef B200RT_DIAG  // tools/gemm_diag.py only: 1 = no TMA loads, 2 = no MMA; high nibble = ring length
+    const int nstages = (dbg_mode >> 4) ? (dbg_mode >> 4) : STAGES;
     const int dmode = dbg_mode & 0xF;
+#else
+    constexpr int nstages = STAGES;
+    constexpr int dmode = 0;
+#endif
     // staging-buffer fills per tile per column half: fp32 [128x32] x 4, or fp16 [128x64] x 2
     constexpr int NBUF_PER_TILE = (EPI == EPI_BIAS_RES_F32) ? 4 : 2;
 

@@ -103,11 +103,16 @@ class Obj:
             o = self._cls.options
             user_marks = marks(self._cls.user_cls)
             max_inputs = user_marks.get("max_inputs") or o.get("max_inputs") or o.get("allow_concurrent_inputs") or 1
-            conc = (o.get("max_containers") or o.get("concurrency_limit") or 1) * max_inputs
+            # One in-box instance stands in for the whole container pool (the reference's containers each run @enter --
+            # e.g. spawn a server on a fixed port -- so N instances in one box would collide).  A class that opted into
+            # input concurrency (@modal.concurrent / max_inputs > 1) declared its methods safe to overlap on one `self`:
+            # it gets max_containers x max_inputs calls in flight.  A class that did not is never entered concurrently
+            # (the reference guarantees one input per container): its calls are serialised on the single instance.
+            conc = (o.get("max_containers") or o.get("concurrency_limit") or 1) * max_inputs if max_inputs > 1 else 1
             env = dict(getattr(o.get("image"), "_env", {}) or {})
             for s in o.get("secrets") or []:
                 env.update(getattr(s, "_env", {}))
-            self._executor = rt.Executor(self._cls.user_cls.__name__, max(conc, 4), env)
+            self._executor = rt.Executor(self._cls.user_cls.__name__, conc, env)
         return self._executor
 
     def _instance(self):

@@ -203,12 +203,20 @@ class Function:
                     yield loop.submit(agen.__anext__()).result()
                 except StopAsyncIteration:
                     return
-        tok = rt._in_worker.set(True)
-        try:
-            gen = self.raw_f(*call_args, **kwargs)
-        finally:
-            rt._in_worker.reset(tok)
-        yield from gen
+        # the body of a sync generator runs inside next(): is_local() must read False there too
+        gen = None
+        while True:
+            tok = rt._in_worker.set(True)
+            try:
+                if gen is None:
+                    gen = self.raw_f(*call_args, **kwargs)
+                try:
+                    v = next(gen)
+                except StopIteration:
+                    return
+            finally:
+                rt._in_worker.reset(tok)
+            yield v
 
     async def _remote_gen_aio(self, *args, **kwargs):
         call_args = self._call_args(args)

@@ -29,7 +29,7 @@ def parse_args(argv):
     ap.add_argument("--pooling", default="cls")
     ap.add_argument("--auto-truncate", action="store_true")
     ap.add_argument("--tokenizer-vocab", default=os.environ.get("B200RT_VOCAB"))
-    ap.add_argument("--weights", default=os.environ.get("B200RT_WEIGHTS"), help="flat fp32 blob (DESIGN.md §3); default: seeded random init")
+    ap.add_argument("--weights", default=os.environ.get("B200RT_WEIGHTS"), help="flat fp32 blob (DESIGN.md §3), a .safetensors checkpoint or an HF snapshot directory; default: the hub cache, else seeded random init")
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("B200RT_GPUS", "0")), help="0 = all visible")
     args, unknown = ap.parse_known_args(argv)
     if unknown:
@@ -38,17 +38,31 @@ def parse_args(argv):
 
 
 def random_blob(seed=0):
-    import numpy as np
+    """Seeded BGE-base-geometry weights (the one definition lives in b200rt.weights)."""
+    from b200rt.weights import random_blob as rb
 
-    rng = np.random.default_rng(seed)
-    g = GEOMETRY
-    h, i = g["hidden"], g["inter"]
-    n = lambda k: rng.standard_normal(k, dtype=np.float32) * np.float32(0.02)  # noqa: E731
-    parts = [n((g["vocab"] + g["max_pos"] + g["type_vocab"]) * h), np.ones(h, np.float32), np.zeros(h, np.float32)]
-    for _ in range(g["layers"]):
-        parts += [n(3 * h * h), np.zeros(3 * h, np.float32), n(h * h), np.zeros(h, np.float32), np.ones(h, np.float32), np.zeros(h, np.float32),
-                  n(i * h), np.zeros(i, np.float32), n(h * i), np.zeros(h, np.float32), np.ones(h, np.float32), np.zeros(h, np.float32)]
-    return np.concatenate(parts)
+    return rb(GEOMETRY, seed)
+
+
+def load_weights(args):
+    """Weights for --model-id: an explicit --weights file (flat fp32 blob, or a .safetensors checkpoint), else the HF
+    hub snapshot under --huggingface-hub-cache (what the reference's `download_model` leaves there:
+    text_embeddings_inference.py:54-56), else seeded random init with a loud notice (no network in this box)."""
+    import numpy as np
+    from b200rt import weights as W
+
+    if args.weights:
+        if args.weights.endswith(".safetensors"):
+            return W.load_safetensors(args.weights) + (f"safetensors {args.weights}",)
+        if os.path.isdir(args.weights):
+            return W.load_hf_dir(args.weights) + (f"HF directory {args.weights}",)
+        return dict(GEOMETRY), np.fromfile(args.weights, np.float32), f"flat blob {args.weights}"
+    cache = args.huggingface_hub_cache or os.environ.get("HUGGINGFACE_HUB_CACHE") or os.environ.get("HF_HUB_CACHE")
+    if cache:
+        snap = W.resolve_hub_snapshot(cache, args.model_id)
+        if snap:
+            return W.load_hf_dir(snap) + (f"hub snapshot {snap}",)
+    return dict(GEOMETRY), random_blob(), None
 
 
 class Engine:
@@ -70,15 +84,18 @@ class Engine:
 
             n_gpus = max(1, torch.cuda.device_count())
         b200rt.init(n_gpus)
-        blob = np.fromfile(args.weights, np.float32) if args.weights else random_blob()
-        if not args.weights:
+        geometry, blob, source = load_weights(args)
+        if source is None:
             print(f"[text-embeddings-router/b200] no weights for {args.model_id!r} offline: seeded random init", file=sys.stderr)
-        self.model = b200rt.EmbedModel(GEOMETRY, blob)
+        else:
+            print(f"[text-embeddings-router/b200] weights: {source}", file=sys.stderr)
+        self.geometry = geometry
+        self.model = b200rt.EmbedModel(geometry, blob)
         self.n_gpus = n_gpus
 
     def embed(self, inputs):
         np = self.np
-        rows = [self.tok.encode(t, GEOMETRY["max_pos"], self.args.auto_truncate) for t in inputs]
+        rows = [self.tok.encode(t, self.geometry["max_pos"], self.args.auto_truncate) for t in inputs]
         lens = np.array([len(r) for r in rows], np.int32)
         ids = np.zeros((len(rows), int(lens.max())), np.int32)
         for i, r in enumerate(rows):
