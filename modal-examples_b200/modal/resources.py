@@ -1,7 +1,7 @@
 """Volume / Secret / Dict / Queue / schedules / retries: the non-compute objects scripts construct at import
 time.  Volumes map to local directories under ``$MODAL_SHIM_STATE`` (default ``~/.modal_b200``); absolute mount
-points such as ``/data`` (text_embeddings_inference.py:27,144) are only materialised as symlinks when
-``MODAL_SHIM_LINK_MOUNTS=1`` -- the runtime does not touch paths outside its state dir by default.  Dict and
+points such as ``/data`` (text_embeddings_inference.py:27,144) resolve into them through virtual mounts
+(``_mounts.py``) -- the runtime does not touch paths outside its state dir (``MODAL_SHIM_MOUNTS=link`` symlinks instead).  Dict and
 Queue are in-process (09_job_queues is OUT OF SCOPE, this is the minimum for scripts to import and run locally)."""
 from __future__ import annotations
 
@@ -58,17 +58,11 @@ class Volume:
         return cm()
 
     def mount_at(self, path) -> bool:
-        """Materialise ``volumes={path: vol}`` when allowed; returns whether ``path`` now points at the volume."""
-        path = str(path)
-        if os.environ.get("MODAL_SHIM_LINK_MOUNTS") != "1":
-            return os.path.exists(path)
-        if os.path.islink(path) or os.path.exists(path):
-            return True
-        try:
-            os.symlink(self.local_path, path)
-            return True
-        except OSError:
-            return False
+        """Materialise ``volumes={path: vol}``: a virtual mount by default (see ``_mounts``), a symlink under
+        ``MODAL_SHIM_MOUNTS=link``; returns whether ``path`` now resolves into the volume."""
+        from . import _mounts
+
+        return _mounts.register(path, self.local_path)
 
     def commit(self):
         return None

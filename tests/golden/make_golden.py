@@ -24,6 +24,9 @@ CASES = {
     "C": (2, "trained", 3, ("ragged", 3, 200, 5, 3)),
     "D": (12, "hf", 0, ("full", 2, 512, 0)),
     "E": (12, "trained", 0, ("ragged", 4, 512, 1, 16)),
+    # trained-like statistics (outlier channels, peaked attention, large LayerNorm gains): see oracle make_weights("hard")
+    "F": (12, "hard", 0, ("ragged", 4, 512, 2, 64)),
+    "G": (2, "hard", 1, ("ragged", 3, 200, 4, 8)),
 }
 
 

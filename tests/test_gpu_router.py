@@ -52,31 +52,137 @@ def router():
     proc.wait(timeout=60)
 
 
-def test_embed_contract_and_parity_with_direct_engine(router):
-    import b200rt
-    from tei_router.server import GEOMETRY, random_blob
+def _encode(texts):
     from tei_router.tokenizer import WordPiece
 
+    tok = WordPiece()
+    rows = [tok.encode(t, 512, True) for t in texts]
+    lens = np.array([len(r) for r in rows], np.int32)
+    ids = np.zeros((len(rows), int(lens.max())), np.int32)
+    for i, r in enumerate(rows):
+        ids[i, : len(r)] = r
+    return ids, lens
+
+
+def _oracle_model():
+    """HF BertModel fp32 (oracle) on the weights the router falls back to offline: seeded HF-default init, seed 0."""
+    import torch
+    from oracle import bge_ref as R
+
+    torch.set_num_threads(min(32, os.cpu_count() or 8))
+    return R, R.build_hf_model(R.make_weights(R.BGE_BASE, 0, "hf"), R.BGE_BASE)
+
+
+def test_embed_contract_and_parity_with_the_oracle(router):
+    """POST /embed against the ORACLE (not against this library's own C ABI): the router's WordPiece ids through HF
+    BertModel fp32 + CLS pooling + L2 normalise on the host, bar 1e-3 relative L2 per item."""
     texts = [f"Show HN: item {i} embeds {'very ' * (i % 7)}long sentences on eight B200s, naïve café #{i}!" for i in range(32)]
     status, out = _post(router, {"inputs": texts})
     assert status == 200 and len(out) == 32 and all(len(v) == 768 for v in out)
     got = np.array(out, np.float32)
     assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
-    # the same token ids through the C ABI in this process must give the same vectors (same weights, same kernels)
-    b200rt.init(devices=[0])
-    model = b200rt.EmbedModel(GEOMETRY, random_blob())
-    tok = WordPiece()
-    rows = [tok.encode(t, 512, True) for t in texts]
-    lens = np.array([len(r) for r in rows], np.int32)
-    ids = np.zeros((32, int(lens.max())), np.int32)
-    for i, r in enumerate(rows):
-        ids[i, : len(r)] = r
-    direct = model.embed(ids, lens)
-    assert np.abs(direct - got).max() < 1e-6
-    b200rt.shutdown()
-    # a single string is accepted like a list of one
+    R, hf = _oracle_model()
+    ids, lens = _encode(texts)
+    ref = R.forward_hf(hf, ids, lens)
+    assert R.rel_l2(got, ref).max() <= 1e-3
+    # a single string is accepted like a list of one, and gives the vector it had inside the batch
     status, one = _post(router, {"inputs": texts[3]})
-    assert status == 200 and np.abs(np.array(one[0], np.float32) - got[3]).max() < 1e-6
+    assert status == 200 and np.abs(np.array(one[0], np.float32) - got[3]).max() < 1e-5
+
+
+DRIVER = '''
+# The call sequence of the reference's text_embeddings_inference.py (spawn the router, wait for the port, POST batches of 32
+# from an @app.cls method, fan out with .map(order_outputs=False)), written out here because /root/reference does not exist on
+# the GPU box; the reference file itself runs verbatim in tests/test_graded_script.py.  Unlike the reference this driver
+# keeps what .map() yields and dumps it for the test.
+import json, os, socket, subprocess, sys
+import modal
+
+PORT = int(os.environ["DRV_PORT"])
+app = modal.App("tei-flow-check")
+vol = modal.Volume.from_name("tei-hn-data", create_if_missing=True)
+
+with modal.Image.debian_slim().imports():
+    from httpx import AsyncClient
+
+
+@app.cls(gpu="B200", max_containers=2)
+@modal.concurrent(max_inputs=6)
+class Tei:
+    @modal.enter()
+    def up(self):
+        self.proc = subprocess.Popen(["text-embeddings-router", "--model-id", "BAAI/bge-base-en-v1.5", "--port", str(PORT)])
+        while True:
+            try:
+                socket.create_connection(("127.0.0.1", PORT), timeout=1).close()
+                break
+            except (socket.timeout, ConnectionRefusedError):
+                if self.proc.poll() is not None:
+                    raise RuntimeError(f"launcher exited unexpectedly with code {self.proc.returncode}")
+        self.client = AsyncClient(base_url=f"http://127.0.0.1:{PORT}", timeout=300)
+
+    @modal.exit()
+    def down(self):
+        self.proc.terminate()
+
+    @modal.method()
+    async def embed(self, batch):
+        ids, texts = zip(*batch)
+        resp = await self.client.post("/embed", json={"inputs": texts})
+        resp.raise_for_status()
+        return list(zip(ids, resp.json()))
+
+
+@app.function(volumes={"/data": vol})
+def run():
+    data = json.load(open("/data/dataset.jsonl"))
+
+    def batches():
+        b = []
+        for item in data:
+            b.append(item)
+            if len(b) == 32:
+                yield b
+                b = []
+
+    got = {}
+    for out in Tei().embed.map(batches(), order_outputs=False):
+        for i, v in out:
+            got[int(i)] = v
+    json.dump(got, open(os.environ["DRV_OUT"], "w"))
+    return len(got)
+'''
+
+
+@pytest.mark.timeout(900)
+def test_map_fan_out_against_the_router_end_to_end(tmp_path):
+    """modal run -> @app.cls @enter spawns the router -> .map(order_outputs=False) of 32-item batches -> POST /embed ->
+    b200rt on the GPU(s): item count (remainder dropped) and vectors against the oracle on the router's token ids."""
+    import json as js
+    import sys
+
+    port = _free_port()
+    state = tmp_path / "state"
+    script = tmp_path / "tei_flow.py"
+    script.write_text(DRIVER)
+    out = tmp_path / "out.json"
+    env = dict(os.environ, PATH=os.path.join(PKG, "bin") + os.pathsep + os.environ["PATH"], PYTHONPATH=PKG + os.pathsep + os.environ.get("PYTHONPATH", ""),
+               MODAL_SHIM_STATE=str(state), DRV_PORT=str(port), DRV_OUT=str(out), B200RT_GPUS="0")
+    rows = 32 * 9 + 7
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_hn_dataset.py"), "--rows", str(rows)], env=env, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([sys.executable, "-m", "modal", "run", f"{script}::run"], env=env, capture_output=True, text=True, timeout=840)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-4000:])
+    got = js.load(open(out))
+    assert len(got) == 32 * 9, "nine full batches; the 7-item remainder is dropped"
+    data = js.load(open(state / "volumes" / "tei-hn-data" / "dataset.jsonl"))
+    assert sorted(int(k) for k in got) == [i for i, _ in data[: 32 * 9]]
+    R, hf = _oracle_model()
+    pick = [0, 1, 31, 32, 100, 287]
+    ids, lens = _encode([data[i][1] for i in pick])
+    ref = R.forward_hf(hf, ids, lens)
+    mine = np.array([got[str(data[i][0])] for i in pick], np.float32)
+    assert R.rel_l2(mine, ref).max() <= 1e-3
 
 
 def test_error_behaviour(router):

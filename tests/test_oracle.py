@@ -32,7 +32,7 @@ def test_param_count_and_blob_layout():
     assert g.flops_per_item(512) == pytest.approx(96.64e9, rel=1e-3)
 
 
-@pytest.mark.parametrize("case", ["A", "B", "C"])
+@pytest.mark.parametrize("case", ["A", "B", "C", "G"])
 def test_numpy_restatement_matches_golden(golden, case):
     layers, style, wseed, spec = mg.CASES[case]
     g, flat = weights(layers, style, wseed)
@@ -42,7 +42,7 @@ def test_numpy_restatement_matches_golden(golden, case):
     assert int(ids.astype(np.int64).sum()) == int(golden[f"{case}_ids_sum"][0])
     emb = R.forward_np(flat, ids, lens, g, dtype=np.float64)
     rel = R.rel_l2(emb, golden[f"{case}_emb"])
-    assert rel.max() < 5e-6, rel  # fp64 restatement vs HF fp32
+    assert rel.max() < (2e-5 if style == "hard" else 5e-6), rel  # fp64 restatement vs HF fp32 (the trained-like style amplifies fp32 rounding ~4x)
     assert np.allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-6)
 
 
