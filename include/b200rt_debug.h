@@ -12,10 +12,17 @@ extern "C" {
 
 /* out[M,N] = epi(A[M,K] . W[N,K]^T + bias (+ resid)) on replica 0.  a, w: fp16 bit patterns (uint16),
  * bias fp32 [N], resid fp32 [M,N] or NULL.  epi: 0 bias->fp16 out, 1 bias+gelu->fp16 out, 2 bias+resid->fp32
- * out.  out is uint16 [M,N] for epi 0/1 and float [M,N] for epi 2.  ms_out (optional): device time of
- * `iters` back-to-back launches divided by iters.                                                    */
+ * out (the residual travels through the kernel as fp16 hi + fp16 lo; out = hi + lo).  out is uint16 [M,N] for epi 0/1
+ * and float [M,N] for epi 2.  ms_out (optional): device time of `iters` back-to-back launches divided by iters.
+ * LayerNorm in the epilogue (optional; all NULL = none): ln_stats = [M][parts] (sum, M2) float pairs, one per 128 columns
+ * of the LayerNorm'd row (parts = K/128 for epi 0/1, N/128 for epi 2).
+ *   epi 0/1: `a` is the PRE-LayerNorm row in fp16, `w` = fp16(gamma o W with every row centred: sum_k w[n,k] = 0),
+ *            bias = W beta + b:  out = epi(rstd * acc + bias)
+ *   epi 2  : out = acc + bias + ((resid - mean) * rstd * ln_gamma + ln_beta); stats_out (optional) receives [M][N/128]
+ *            (sum, M2) partials of the new rows.                                                             */
 int b200rt_debug_gemm(int epi, const uint16_t* a, const uint16_t* w, const float* bias, const float* resid,
-                      void* out, int M, int N, int K, int iters, float* ms_out);
+                      void* out, int M, int N, int K, int iters, float* ms_out, const float* ln_stats,
+                      const float* ln_gamma, const float* ln_beta, float eps, float* stats_out);
 
 /* ctx[B*S,768] (fp16 bits) = multi-head attention over qkv[B*S,2304] (fp16 bits), lens[B].           */
 int b200rt_debug_attention(const uint16_t* qkv, const int32_t* lens, uint16_t* ctx, int B, int S, int iters,

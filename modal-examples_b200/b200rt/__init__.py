@@ -88,7 +88,8 @@ def load_library():
         lib.b200rt_last_error.restype = ctypes.c_char_p
         lib.b200rt_shutdown.restype = None
         lib.b200rt_debug_gemm.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
-                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, f32p]
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, f32p, ctypes.c_void_p,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p]
         lib.b200rt_debug_attention.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, f32p]
         lib.b200rt_debug_hidden.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         lib.b200rt_debug_profile_forward.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t,
@@ -298,19 +299,24 @@ def device_sync(gpu: int = 0):
     _check(load_library().b200rt_device_sync(gpu))
 
 
-def debug_gemm(epi: int, a16: np.ndarray, w16: np.ndarray, bias: np.ndarray, resid=None, iters: int = 1):
-    """a16 [M,K], w16 [N,K] float16; returns (out, ms)."""
+def debug_gemm(epi: int, a16: np.ndarray, w16: np.ndarray, bias: np.ndarray, resid=None, iters: int = 1, ln_stats=None,
+               ln_gamma=None, ln_beta=None, eps: float = 1e-12, want_stats: bool = False):
+    """a16 [M,K], w16 [N,K] float16; returns (out, ms) -- or (out, ms, stats_out [M, N/128, 2]) with ``want_stats`` (epi 2).
+    ``ln_stats`` [M, parts, 2] (sum, M2) partials switch the LayerNorm epilogues on (see include/b200rt_debug.h)."""
     a16 = np.ascontiguousarray(a16, dtype=np.float16)
     w16 = np.ascontiguousarray(w16, dtype=np.float16)
     bias = np.ascontiguousarray(bias, dtype=np.float32)
     M, K = a16.shape
     N = w16.shape[0]
     out = np.empty((M, N), np.float32 if epi == 2 else np.float16)
-    r = np.ascontiguousarray(resid, dtype=np.float32) if resid is not None else None
+    c32 = lambda v: np.ascontiguousarray(v, dtype=np.float32) if v is not None else None  # noqa: E731
+    r, st, lg, lb = c32(resid), c32(ln_stats), c32(ln_gamma), c32(ln_beta)
+    so = np.zeros((M, N // 128, 2), np.float32) if want_stats else None
+    p = lambda v: _ptr(v) if v is not None else None  # noqa: E731
     ms = ctypes.c_float(0)
-    _check(load_library().b200rt_debug_gemm(epi, _ptr(a16), _ptr(w16), _ptr(bias), _ptr(r) if r is not None else None, _ptr(out), M, N, K,
-                                            iters, ctypes.byref(ms)))
-    return out, ms.value
+    _check(load_library().b200rt_debug_gemm(epi, _ptr(a16), _ptr(w16), _ptr(bias), p(r), _ptr(out), M, N, K, iters, ctypes.byref(ms),
+                                            p(st), p(lg), p(lb), eps, p(so)))
+    return (out, ms.value, so) if want_stats else (out, ms.value)
 
 
 def debug_attention(qkv16: np.ndarray, lens: np.ndarray, B: int, S: int, iters: int = 1):

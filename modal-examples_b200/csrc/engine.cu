@@ -97,16 +97,16 @@ int make_map_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, 
     return 0;
 }
 
-// fp32 2D row-major [rows, cols] -> box {32, 128} (128-byte rows), 128B swizzle: epilogue staging tiles
-int make_map_2d_f32(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols) {
+// fp16 2D row-major [rows, cols] -> box {32, 128} (64-byte rows), 64B swizzle: the residual epilogue's hi / lo staging chunks
+int make_map_2d_chunk(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols) {
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {cols * 4};
+    cuuint64_t strides[1] = {cols * 2};
     cuuint32_t box[2] = {32, 128};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, es,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(B200RT_E_CUDA, "cuTensorMapEncodeTiled(f32 %llu x %llu) -> %d",
+    if (r != CUDA_SUCCESS) return fail(B200RT_E_CUDA, "cuTensorMapEncodeTiled(chunk %llu x %llu) -> %d",
                                        (unsigned long long)rows, (unsigned long long)cols, (int)r);
     return 0;
 }
@@ -135,6 +135,9 @@ constexpr int MAX_SEQ = 512;
 struct LayerW {
     __half *qkv_w, *ao_w, *ff1_w, *ff2_w;
     float *qkv_b, *ao_b, *ln1_g, *ln1_b, *ff1_b, *ff2_b, *ln2_g, *ln2_b;
+    // LayerNorm folded into the consuming projections at load time (kernels.h):
+    // qkv_w / ff1_w hold fp16(gamma o W, rows centred); *_c = W beta + b
+    float *qkv_c, *ff1_c;
     CUtensorMap m_qkv, m_ao, m_ff1, m_ff2;  // box {64,128}: each CTA of a pair stages half of the tile's columns
 };
 
@@ -156,13 +159,13 @@ struct Dev {
     int sm_count = 148;
     cudaStream_t compute = nullptr;
     // workspace (capacity cap_rows rows)
-    float* y32 = nullptr;        // fp32 residual stream, PRE-LayerNorm
-    float2* stats = nullptr;     // (mean, rstd) per row of the LayerNorm last applied to y32
+    __half *yhi = nullptr, *ylo = nullptr;  // residual stream y = hi + lo, PRE-LayerNorm; hi doubles as the GEMM A operand
+    float2* pstats[2] = {nullptr, nullptr};  // [rows][STAT_PARTS] (sum, M2) partials: [0] embedding LN / LN2 inputs, [1] LN1 inputs
     float* x32_dbg = nullptr;    // tests only (b200rt_debug_hidden): normalised fp32 rows, allocated on first use
-    __half *x16 = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr;
-    CUtensorMap m_x16, m_ctx, m_ffn;      // fp16 [rows,*] box {64,128}: GEMM A operands (m_ffn is also FFN1's output map)
+    __half *qkv = nullptr, *ctx = nullptr, *ffn = nullptr;
+    CUtensorMap m_yhi, m_ctx, m_ffn;      // fp16 [rows,*] box {64,128}: GEMM A operands (m_ffn is also FFN1's output map)
     CUtensorMap m_qkv2d;                  // fp16 [rows,2304] box {64,128}: QKV GEMM output
-    CUtensorMap m_y32;                    // fp32 [rows,768] box {32,128}: the fp32 epilogues update y32 in place
+    CUtensorMap m_yhi_c, m_ylo_c;         // fp16 [rows,768] box {32,128} SW64: the residual epilogues update hi / lo in place
     std::unordered_map<int, std::pair<CUtensorMap, CUtensorMap>> m_qkv_by_S;  // (qkv, ctx) 3D maps per padded length
     // wave input slots (written by the root's scatter kernel, possibly over NVLink)
     int32_t* ids_in[NSLOT] = {};
@@ -170,7 +173,7 @@ struct Dev {
     cudaEvent_t ev_done[NSLOT];
     cudaEvent_t ev_begin[NSLOT], ev_end[NSLOT];  // timing: the forward itself on this replica's compute stream
     std::mutex mu;  // serialises host-side enqueue on this replica (scheduler vs. embed_device/debug)
-    // Every forward on this replica uses the same workspace (y32, x16, qkv, ctx, ffn, stats), whichever stream it is
+    // Every forward on this replica uses the same workspace (yhi, ylo, qkv, ctx, ffn, pstats), whichever stream it is
     // enqueued on: ev_ws is recorded behind each forward and waited on ahead of the next one, so forwards from the
     // scheduler's stream and from callers' streams (b200rt_embed_device) execute one after the other on the device.
     cudaEvent_t ev_ws = nullptr;
@@ -298,34 +301,37 @@ int forward_enqueue(Dev& d, const Model& m, int dev_index, const int32_t* ids, c
     };
     mark("begin");
     float* const dbg = full ? nullptr : d.x32_dbg;
-    CUDA_TRY(launch_embed_ln(ids, w.word, w.pos, w.type, w.emb_g, w.emb_b, d.y32, d.x16, d.stats, L == 0 ? dbg : nullptr, M, S, c.vocab, c.eps, stream));
-    LnRef prev{d.stats, w.emb_g, w.emb_b};  // the LayerNorm whose output is the current residual
-    ++nl; mark("embed_ln");
+    CUDA_TRY(launch_embed(ids, w.word, w.pos, w.type, d.yhi, d.ylo, d.pstats[0], M, S, c.vocab, stream));
+    ++nl; mark("embed");
+    const float *prev_g = w.emb_g, *prev_b = w.emb_b;  // the LayerNorm that applies to the current residual rows
     for (int l = 0; l < L; ++l) {
         const LayerW& lw = w.layers[l];
-        CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_x16, lw.m_qkv, d.m_qkv2d, nullptr, lw.qkv_b, M, QKV_DIM, HIDDEN, d.sm_count, stream));
+        // QKV = LN_prev(y) Wqkv^T + b, the LayerNorm folded into the epilogue
+        GemmEpi e_qkv{lw.qkv_c, d.pstats[0], STAT_PARTS, nullptr, nullptr, nullptr, c.eps};
+        CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_yhi, lw.m_qkv, d.m_qkv2d, nullptr, e_qkv, M, QKV_DIM, HIDDEN, d.sm_count, stream));
         ++nl; mark("gemm_qkv");
         CUDA_TRY(launch_attention(*mq, *mc, lens, B, S, stream));
         ++nl; mark("attention");
-        CUDA_TRY(launch_gemm(EPI_BIAS_RES_F32, d.m_ctx, lw.m_ao, d.m_y32, &prev, lw.ao_b, M, HIDDEN, HIDDEN, d.sm_count, stream));
+        // y <- ctx Wao^T + b + LN_prev(y); new row statistics (LN1's) into pstats[1]
+        GemmEpi e_ao{lw.ao_b, d.pstats[0], STAT_PARTS, prev_g, prev_b, d.pstats[1], c.eps};
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_SPLIT, d.m_ctx, lw.m_ao, d.m_yhi_c, &d.m_ylo_c, e_ao, M, HIDDEN, HIDDEN, d.sm_count, stream));
         ++nl; mark("gemm_attn_out");
-        CUDA_TRY(launch_ln(d.y32, lw.ln1_g, lw.ln1_b, d.x16, d.stats, nullptr, M, c.eps, stream));
-        prev = LnRef{d.stats, lw.ln1_g, lw.ln1_b};
-        ++nl; mark("ln1");
-        CUDA_TRY(launch_gemm(EPI_BIAS_GELU_F16, d.m_x16, lw.m_ff1, d.m_ffn, nullptr, lw.ff1_b, M, c.inter, HIDDEN, d.sm_count, stream));
+        GemmEpi e_ff1{lw.ff1_c, d.pstats[1], STAT_PARTS, nullptr, nullptr, nullptr, c.eps};
+        CUDA_TRY(launch_gemm(EPI_BIAS_GELU_F16, d.m_yhi, lw.m_ff1, d.m_ffn, nullptr, e_ff1, M, c.inter, HIDDEN, d.sm_count, stream));
         ++nl; mark("gemm_ffn1_gelu");
-        CUDA_TRY(launch_gemm(EPI_BIAS_RES_F32, d.m_ffn, lw.m_ff2, d.m_y32, &prev, lw.ff2_b, M, HIDDEN, c.inter, d.sm_count, stream));
+        // y <- ffn W2^T + b + LN1(y); LN2's statistics into pstats[0]
+        GemmEpi e_ff2{lw.ff2_b, d.pstats[1], STAT_PARTS, lw.ln1_g, lw.ln1_b, d.pstats[0], c.eps};
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_SPLIT, d.m_ffn, lw.m_ff2, d.m_yhi_c, &d.m_ylo_c, e_ff2, M, HIDDEN, c.inter, d.sm_count, stream));
         ++nl; mark("gemm_ffn2");
-        if (!(full && l == L - 1)) {
-            CUDA_TRY(launch_ln(d.y32, lw.ln2_g, lw.ln2_b, d.x16, d.stats, l == L - 1 ? dbg : nullptr, M, c.eps, stream));
-            prev = LnRef{d.stats, lw.ln2_g, lw.ln2_b};
-            ++nl; mark("ln2");
-        }
+        prev_g = lw.ln2_g;
+        prev_b = lw.ln2_b;
     }
     if (full) {
-        const LayerW& lw = w.layers[L - 1];
-        CUDA_TRY(launch_pool_normalize(d.y32, lw.ln2_g, lw.ln2_b, out, B, S, c.eps, stream));
+        CUDA_TRY(launch_pool_normalize(d.yhi, d.ylo, prev_g, prev_b, out, B, S, c.eps, stream));
         ++nl; mark("pool_normalize");
+    } else {  // debug: materialise the post-LayerNorm hidden state
+        CUDA_TRY(launch_ln_materialize(d.yhi, d.ylo, prev_g, prev_b, dbg, M, c.eps, stream));
+        ++nl;
     }
     if (launches) *launches += nl;
     return 0;
@@ -783,24 +789,27 @@ int alloc_dev(Runtime& rt, Dev& d) {
     CUDA_TRY(cudaStreamCreateWithFlags(&d.compute, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&d.ev_ws, cudaEventDisableTiming));
     const size_t R = rt.cap_rows;
-    CUDA_TRY(cudaMalloc(&d.stats, R * sizeof(float2)));
-    CUDA_TRY(cudaMemset(d.stats, 0, R * sizeof(float2)));
-    CUDA_TRY(cudaMalloc(&d.y32, R * HIDDEN * 4));
-    CUDA_TRY(cudaMalloc(&d.x16, R * HIDDEN * 2));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaMalloc(&d.pstats[i], R * STAT_PARTS * sizeof(float2)));
+        CUDA_TRY(cudaMemset(d.pstats[i], 0, R * STAT_PARTS * sizeof(float2)));
+    }
+    CUDA_TRY(cudaMalloc(&d.yhi, R * HIDDEN * 2));
+    CUDA_TRY(cudaMalloc(&d.ylo, R * HIDDEN * 2));
     CUDA_TRY(cudaMalloc(&d.qkv, R * QKV_DIM * 2));
     CUDA_TRY(cudaMalloc(&d.ctx, R * HIDDEN * 2));
     CUDA_TRY(cudaMalloc(&d.ffn, R * 3072 * 2));
     // padded / stale rows must stay finite (0 * NaN would leak through masked attention probabilities)
-    CUDA_TRY(cudaMemset(d.y32, 0, R * HIDDEN * 4));
-    CUDA_TRY(cudaMemset(d.x16, 0, R * HIDDEN * 2));
+    CUDA_TRY(cudaMemset(d.yhi, 0, R * HIDDEN * 2));
+    CUDA_TRY(cudaMemset(d.ylo, 0, R * HIDDEN * 2));
     CUDA_TRY(cudaMemset(d.qkv, 0, R * QKV_DIM * 2));
     CUDA_TRY(cudaMemset(d.ctx, 0, R * HIDDEN * 2));
     CUDA_TRY(cudaMemset(d.ffn, 0, R * 3072 * 2));
-    if (int rc = make_map_2d(&d.m_x16, d.x16, R, HIDDEN, 128)) return rc;
+    if (int rc = make_map_2d(&d.m_yhi, d.yhi, R, HIDDEN, 128)) return rc;
     if (int rc = make_map_2d(&d.m_ctx, d.ctx, R, HIDDEN, 128)) return rc;
     if (int rc = make_map_2d(&d.m_ffn, d.ffn, R, 3072, 128)) return rc;
     if (int rc = make_map_2d(&d.m_qkv2d, d.qkv, R, QKV_DIM, 128)) return rc;
-    if (int rc = make_map_2d_f32(&d.m_y32, d.y32, R, HIDDEN)) return rc;
+    if (int rc = make_map_2d_chunk(&d.m_yhi_c, d.yhi, R, HIDDEN)) return rc;
+    if (int rc = make_map_2d_chunk(&d.m_ylo_c, d.ylo, R, HIDDEN)) return rc;
     for (int s = 0; s < NSLOT; ++s) {
         CUDA_TRY(cudaMalloc(&d.ids_in[s], R * 4));
         CUDA_TRY(cudaMalloc(&d.lens_in[s], R * 4));
@@ -896,11 +905,15 @@ int model_load(const b200rt_bert_config& c, const float* blob, size_t nbytes, in
 
     auto m = std::make_unique<Model>();
     m->cfg = c;
-    m->f32_elems = emb + static_cast<size_t>(c.layers) * per_layer_p;
+    const size_t per_layer_x = 3 * H + I;  // derived vectors: qkv_c, ff1_c
+    const size_t blob_f32 = emb + static_cast<size_t>(c.layers) * per_layer_p;
+    m->f32_elems = blob_f32 + static_cast<size_t>(c.layers) * per_layer_x;
     m->f16_elems = static_cast<size_t>(c.layers) * per_layer_w;
     m->per_dev.resize(rt.devs.size());
 
-    // root: upload the fp32 blob once, carve fp32 params / convert GEMM weights to fp16 on the GPU
+    // root: upload the fp32 blob once, carve fp32 params / convert GEMM weights to fp16 on the GPU.  The LayerNorm in front of
+    // a projection is folded into it here (kernels.h): QKV of layer l takes the previous layer's LN2 (the embedding LN for
+    // l = 0), FFN1 takes the layer's own LN1.
     Dev& root = *rt.devs[0];
     std::lock_guard<std::mutex> dl(root.mu);
     CUDA_TRY(cudaSetDevice(root.id));
@@ -915,23 +928,37 @@ int model_load(const b200rt_bert_config& c, const float* blob, size_t nbytes, in
     CUDA_TRY(cudaSetDevice(root.id));
     DevWeights& rw = m->per_dev[0];
     {
-        size_t src = 0, o32 = 0, o16 = 0;
+        size_t src = 0, o32 = 0, o16 = 0, ox = blob_f32;
         auto take32 = [&](size_t n) -> cudaError_t {
             cudaError_t e = cudaMemcpyAsync(rw.f32_arena + o32, d_blob + src, n * 4, cudaMemcpyDeviceToDevice, root.compute);
             src += n; o32 += n;
             return e;
         };
-        auto take16 = [&](size_t n) -> cudaError_t {
-            cudaError_t e = launch_f32_to_f16(d_blob + src, rw.f16_arena + o16, n, root.compute);
-            src += n; o16 += n;
+        // W [N,K] at the cursor -> fp16 (gamma folded in and rows centred when given; W beta + b into the derived region)
+        auto take16 = [&](size_t N_, size_t K_, const float* gamma, const float* beta, const float* bias) -> cudaError_t {
+            float* cv = gamma ? rw.f32_arena + ox : nullptr;
+            cudaError_t e = launch_fold_ln(d_blob + src, gamma, beta, bias, rw.f16_arena + o16, cv, static_cast<int>(N_),
+                                           static_cast<int>(K_), root.compute);
+            src += N_ * K_; o16 += N_ * K_;
+            if (gamma) ox += N_;
             return e;
         };
+        const float* ln_g = d_blob + emb - 2 * H;  // the LayerNorm in front of the next QKV: embedding LN first
+        const float* ln_b = d_blob + emb - H;
         CUDA_TRY(take32(emb));
         for (int l = 0; l < c.layers; ++l) {
-            CUDA_TRY(take16(3 * H * H)); CUDA_TRY(take32(3 * H));           // qkv.w, qkv.b
-            CUDA_TRY(take16(H * H));     CUDA_TRY(take32(H + 2 * H));       // ao.w, ao.b, ln1.g, ln1.b
-            CUDA_TRY(take16(I * H));     CUDA_TRY(take32(I));               // ff1.w, ff1.b
-            CUDA_TRY(take16(H * I));     CUDA_TRY(take32(H + 2 * H));       // ff2.w, ff2.b, ln2.g, ln2.b
+            const float* qkv_b = d_blob + src + 3 * H * H;
+            CUDA_TRY(take16(3 * H, H, ln_g, ln_b, qkv_b)); CUDA_TRY(take32(3 * H));      // qkv.w (folded), qkv.b
+            CUDA_TRY(take16(H, H, nullptr, nullptr, nullptr));                            // ao.w
+            const float* ln1_g = d_blob + src + H;
+            const float* ln1_b = d_blob + src + 2 * H;
+            CUDA_TRY(take32(H + 2 * H));                                                  // ao.b, ln1.g, ln1.b
+            const float* ff1_b = d_blob + src + I * H;
+            CUDA_TRY(take16(I, H, ln1_g, ln1_b, ff1_b)); CUDA_TRY(take32(I));            // ff1.w (folded), ff1.b
+            CUDA_TRY(take16(H, I, nullptr, nullptr, nullptr));                            // ff2.w
+            ln_g = d_blob + src + H;                                                      // ln2 of this layer feeds the next QKV
+            ln_b = d_blob + src + 2 * H;
+            CUDA_TRY(take32(H + 2 * H));                                                  // ff2.b, ln2.g, ln2.b
         }
     }
     CUDA_TRY(cudaStreamSynchronize(root.compute));
@@ -960,6 +987,8 @@ int model_load(const b200rt_bert_config& c, const float* blob, size_t nbytes, in
             lw.ao_w = q;  q += H * H;      lw.ao_b = p;  p += H;  lw.ln1_g = p; p += H;  lw.ln1_b = p; p += H;
             lw.ff1_w = q; q += I * H;      lw.ff1_b = p; p += I;
             lw.ff2_w = q; q += H * I;      lw.ff2_b = p; p += H;  lw.ln2_g = p; p += H;  lw.ln2_b = p; p += H;
+            float* x = w.f32_arena + blob_f32 + static_cast<size_t>(l) * per_layer_x;
+            lw.qkv_c = x; lw.ff1_c = x + 3 * H;
             if (int rc = make_map_2d(&lw.m_qkv, lw.qkv_w, 3 * H, H, 128)) return rc;
             if (int rc = make_map_2d(&lw.m_ao, lw.ao_w, H, H, 128)) return rc;
             if (int rc = make_map_2d(&lw.m_ff1, lw.ff1_w, I, H, 128)) return rc;
@@ -1266,7 +1295,7 @@ void b200rt_shutdown(void) {
     for (auto& d : rt->devs) {
         cudaSetDevice(d->id);
         drop_graphs(*d);
-        cudaFree(d->x32_dbg); cudaFree(d->stats); cudaFree(d->y32); cudaFree(d->x16); cudaFree(d->qkv); cudaFree(d->ctx); cudaFree(d->ffn);
+        cudaFree(d->x32_dbg); cudaFree(d->pstats[0]); cudaFree(d->pstats[1]); cudaFree(d->yhi); cudaFree(d->ylo); cudaFree(d->qkv); cudaFree(d->ctx); cudaFree(d->ffn);
         for (int s = 0; s < NSLOT; ++s) { cudaFree(d->ids_in[s]); cudaFree(d->lens_in[s]); cudaEventDestroy(d->ev_done[s]); cudaEventDestroy(d->ev_begin[s]); cudaEventDestroy(d->ev_end[s]); }
         cudaEventDestroy(d->ev_ws);
         cudaStreamDestroy(d->compute);
@@ -1286,63 +1315,102 @@ void b200rt_shutdown(void) {
 // ------------------------------------------------------------------------------------------ debug entry points
 
 int b200rt_debug_gemm(int epi, const uint16_t* a, const uint16_t* w, const float* bias, const float* resid, void* out,
-                      int M, int N, int K, int iters, float* ms_out) {
+                      int M, int N, int K, int iters, float* ms_out, const float* ln_stats,
+                      const float* ln_gamma, const float* ln_beta, float eps, float* stats_out) {
     Runtime* rt = live_rt();
     if (!rt) return g_poisoned.load() ? B200RT_E_CUDA : B200RT_E_STATE;
     if (!a || !w || !bias || !out || M < 1 || N % 256 || K % 64 || epi < 0 || (epi & 0xFF) > 2) return fail(B200RT_E_INVALID, "bad gemm arguments");
-    const int epi_full = epi;  // bits 8+ = diagnostic mode of the pair kernel
+    const int epi_full = epi;  // bits 8+ = diagnostic mode of the pair kernel (B200RT_DIAG builds)
     epi &= 0xFF;
+    if (ln_stats && epi != 2 && K % 128) return fail(B200RT_E_INVALID, "LayerNorm fold needs K % 128 == 0");
+    if (ln_stats && epi == 2 && (!ln_gamma || !ln_beta)) return fail(B200RT_E_INVALID, "LayerNorm re-apply needs gamma and beta");
     Dev& d = *rt->devs[0];
     std::lock_guard<std::mutex> dl(d.mu);
     CUDA_TRY(cudaSetDevice(d.id));
     const size_t Mp = (static_cast<size_t>(M) + 255) / 256 * 256;
-    __half *da = nullptr, *dw = nullptr;
-    float *db = nullptr, *dr = nullptr;
+    const int parts_in = epi == 2 ? N / 128 : K / 128;
+    const int parts_out = N / 128;
+    __half *da = nullptr, *dw = nullptr, *dhi = nullptr, *dlo = nullptr, *dhi0 = nullptr, *dlo0 = nullptr;
+    float *db = nullptr, *dg = nullptr, *dbt = nullptr;
+    float2 *dsi = nullptr, *dso = nullptr;
     void* dout = nullptr;
-    const size_t out_elt = epi == 2 ? 4 : 2;
     CUDA_TRY(cudaMalloc(&da, Mp * K * 2));
     CUDA_TRY(cudaMemset(da, 0, Mp * K * 2));
     CUDA_TRY(cudaMalloc(&dw, static_cast<size_t>(N) * K * 2));
     CUDA_TRY(cudaMalloc(&db, static_cast<size_t>(N) * 4));
-    CUDA_TRY(cudaMalloc(&dout, Mp * N * out_elt));
-    CUDA_TRY(cudaMemset(dout, 0xFF, Mp * N * out_elt));
     CUDA_TRY(cudaMemcpy(da, a, static_cast<size_t>(M) * K * 2, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(dw, w, static_cast<size_t>(N) * K * 2, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(db, bias, static_cast<size_t>(N) * 4, cudaMemcpyHostToDevice));
-    if (epi == 2) {
-        if (!resid) return fail(B200RT_E_INVALID, "epi 2 needs resid");
-        CUDA_TRY(cudaMalloc(&dr, Mp * N * 4));
-        CUDA_TRY(cudaMemset(dr, 0, Mp * N * 4));
-        CUDA_TRY(cudaMemcpy(dr, resid, static_cast<size_t>(M) * N * 4, cudaMemcpyHostToDevice));
+    if (ln_stats) {
+        CUDA_TRY(cudaMalloc(&dsi, Mp * parts_in * sizeof(float2)));
+        CUDA_TRY(cudaMemset(dsi, 0, Mp * parts_in * sizeof(float2)));
+        CUDA_TRY(cudaMemcpy(dsi, ln_stats, static_cast<size_t>(M) * parts_in * sizeof(float2), cudaMemcpyHostToDevice));
     }
-    CUtensorMap ta, tb, tout;
+    auto up = [&](float** dp, const float* h) -> cudaError_t {
+        if (!h) return cudaSuccess;
+        cudaError_t e = cudaMalloc(dp, static_cast<size_t>(N) * 4);
+        return e != cudaSuccess ? e : cudaMemcpy(*dp, h, static_cast<size_t>(N) * 4, cudaMemcpyHostToDevice);
+    };
+    CUDA_TRY(up(&dg, ln_gamma));
+    CUDA_TRY(up(&dbt, ln_beta));
+    CUtensorMap ta, tb, tout, tlo;
     if (int rc = make_map_2d(&ta, da, Mp, K, 128)) return rc;
     if (int rc = make_map_2d(&tb, dw, N, K, 128)) return rc;
+    std::vector<__half> hhi, hlo;
     if (epi == 2) {
-        if (int rc = make_map_2d_f32(&tout, dout, Mp, N)) return rc;
+        if (!resid) return fail(B200RT_E_INVALID, "epi 2 needs resid");
+        // the residual travels as hi + lo (fp16 + fp16): split on the host, keep a pristine copy for the final launch
+        hhi.assign(Mp * N, __float2half_rn(0.f));
+        hlo.assign(Mp * N, __float2half_rn(0.f));
+        for (size_t i = 0; i < static_cast<size_t>(M) * N; ++i) {
+            hhi[i] = __float2half_rn(resid[i]);
+            hlo[i] = __float2half_rn(resid[i] - __half2float(hhi[i]));
+        }
+        for (__half** pp : {&dhi, &dlo, &dhi0, &dlo0}) CUDA_TRY(cudaMalloc(pp, Mp * N * 2));
+        CUDA_TRY(cudaMemcpy(dhi0, hhi.data(), Mp * N * 2, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(dlo0, hlo.data(), Mp * N * 2, cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(dhi, dhi0, Mp * N * 2, cudaMemcpyDeviceToDevice));
+        CUDA_TRY(cudaMemcpy(dlo, dlo0, Mp * N * 2, cudaMemcpyDeviceToDevice));
+        CUDA_TRY(cudaMalloc(&dso, Mp * parts_out * sizeof(float2)));
+        if (int rc = make_map_2d_chunk(&tout, dhi, Mp, N)) return rc;
+        if (int rc = make_map_2d_chunk(&tlo, dlo, Mp, N)) return rc;
     } else {
+        CUDA_TRY(cudaMalloc(&dout, Mp * N * 2));
+        CUDA_TRY(cudaMemset(dout, 0xFF, Mp * N * 2));
         if (int rc = make_map_2d(&tout, dout, Mp, N, 128)) return rc;
     }
-    // epi 2 updates `out` in place (out = acc + bias + out): reload the residual before every launch
+    GemmEpi e{db, dsi, parts_in, dg, dbt, dso, eps};
+    // epi 2 updates hi / lo in place (y = acc + bias + LN(y)): reload the residual before the launch whose result is returned
     auto reload = [&]() -> cudaError_t {
-        return epi == 2 ? cudaMemcpyAsync(dout, dr, Mp * N * 4, cudaMemcpyDeviceToDevice, d.compute) : cudaSuccess;
+        if (epi != 2) return cudaSuccess;
+        cudaError_t ce = cudaMemcpyAsync(dhi, dhi0, Mp * N * 2, cudaMemcpyDeviceToDevice, d.compute);
+        return ce != cudaSuccess ? ce : cudaMemcpyAsync(dlo, dlo0, Mp * N * 2, cudaMemcpyDeviceToDevice, d.compute);
     };
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     if (iters < 1) iters = 1;
     CUDA_TRY(cudaEventRecord(e0, d.compute));
-    for (int i = 0; i < iters; ++i) CUDA_TRY(launch_gemm(epi_full, ta, tb, tout, nullptr, db, M, N, K, d.sm_count, d.compute));  // timing (values drift in place)
+    for (int i = 0; i < iters; ++i) CUDA_TRY(launch_gemm(epi_full, ta, tb, tout, epi == 2 ? &tlo : nullptr, e, M, N, K, d.sm_count, d.compute));  // timing (values drift in place)
     CUDA_TRY(cudaEventRecord(e1, d.compute));
     CUDA_TRY(reload());
-    CUDA_TRY(launch_gemm(epi_full, ta, tb, tout, nullptr, db, M, N, K, d.sm_count, d.compute));  // the result that is returned
+    CUDA_TRY(launch_gemm(epi_full, ta, tb, tout, epi == 2 ? &tlo : nullptr, e, M, N, K, d.sm_count, d.compute));  // the result that is returned
     CUDA_TRY(cudaStreamSynchronize(d.compute));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     if (ms_out) *ms_out = ms / iters;
-    CUDA_TRY(cudaMemcpy(out, dout, static_cast<size_t>(M) * N * out_elt, cudaMemcpyDeviceToHost));
+    if (epi == 2) {
+        CUDA_TRY(cudaMemcpy(hhi.data(), dhi, Mp * N * 2, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(hlo.data(), dlo, Mp * N * 2, cudaMemcpyDeviceToHost));
+        float* o = static_cast<float*>(out);
+        for (size_t i = 0; i < static_cast<size_t>(M) * N; ++i) o[i] = __half2float(hhi[i]) + __half2float(hlo[i]);
+        if (stats_out) CUDA_TRY(cudaMemcpy(stats_out, dso, static_cast<size_t>(M) * parts_out * sizeof(float2), cudaMemcpyDeviceToHost));
+    } else {
+        CUDA_TRY(cudaMemcpy(out, dout, static_cast<size_t>(M) * N * 2, cudaMemcpyDeviceToHost));
+    }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(da); cudaFree(dw); cudaFree(db); cudaFree(dr); cudaFree(dout);
+    cudaFree(da); cudaFree(dw); cudaFree(db); cudaFree(dg); cudaFree(dbt); cudaFree(dsi); cudaFree(dso);
+    cudaFree(dhi); cudaFree(dlo); cudaFree(dhi0); cudaFree(dlo0); cudaFree(dout);
     return 0;
 }
 

@@ -12,10 +12,13 @@
 // lines per warp instruction (32 L1 wavefronts), which made the fp32 residual epilogue LSU-bound.  Instead
 // each column half of the tile (4 warps, thread = row) works on 128-row x 128-byte staging buffers in
 // shared memory (128B-swizzled, so a thread's 16-byte accesses are bank-conflict free per quarter warp):
-//   EPI_BIAS_RES_F32 : a DMA thread TMA-loads the fp32 PRE-LayerNorm residual chunk [128 x 32] of y into the
-//                      buffer, the compute threads re-apply that LayerNorm from the row's (mean, rstd) and
-//                      add accumulator + bias in place, the DMA thread TMA-stores the chunk back to y.
-//   EPI_BIAS(_GELU)_F16 : compute threads write fp16 [128 x 64] chunks, the DMA thread TMA-stores them.
+//   EPI_BIAS_RES_SPLIT : a DMA thread TMA-loads the PRE-LayerNorm residual chunk [128 x 32] of y = hi + lo (two fp16
+//                      arrays, 64-byte rows, 64B swizzle) into the buffer, the compute threads re-apply that LayerNorm
+//                      from the row's statistics, add accumulator + bias, split the new value into hi' + lo' in place
+//                      and accumulate the new row's (sum, M2) partial; the DMA thread TMA-stores both chunks back.
+//   EPI_BIAS(_GELU)_F16 : compute threads apply the folded LayerNorm  rstd * acc + c  (see kernels.h),
+//                      write fp16 [128 x 64] chunks, the DMA thread TMA-stores them.
+// No LayerNorm kernel exists in the product path: the statistics travel as per-128-column partials next to the residual.
 //
 //   full[s]   (leader's)  : leader producer arrive.expect_tx(64 KB); both CTAs' TMA loads complete_tx on it
 //   empty[s]  (per CTA)   : tcgen05.commit multicast to both CTAs once the MMAs that read stage s retire
@@ -64,8 +67,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                 const __grid_constant__ CUtensorMap tma_out, const float* __restrict__ bias, const float2* __restrict__ ln_stats,
-                 const float* __restrict__ ln_gamma, const float* __restrict__ ln_beta, int M, int N, int K, int dbg_mode) {
+                 const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_lo, const GemmEpi ep,
+                 int M, int N, int K, int dbg_mode) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -96,12 +99,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     constexpr int dmode = 0;
 #endif
     // staging-buffer fills per tile per column half: fp32 [128x32] x 4, or fp16 [128x64] x 2
-    constexpr int NBUF_PER_TILE = (EPI == EPI_BIAS_RES_F32) ? 4 : 2;
+    constexpr int NBUF_PER_TILE = (EPI == EPI_BIAS_RES_SPLIT) ? 4 : 2;
+    const float* __restrict__ bias = ep.bias;
 
     if (warp == 0 && elect_one()) {
         prefetch_tmap(&tma_a);
         prefetch_tmap(&tma_b);
         prefetch_tmap(&tma_out);
+        if constexpr (EPI == EPI_BIAS_RES_SPLIT) prefetch_tmap(&tma_lo);
     }
     if (warp == 1 && elect_one()) {
         for (int s = 0; s < STAGES; ++s) {
@@ -192,16 +197,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 const int tile = pair + (g / NBUF_PER_TILE) * num_pairs;
                 const int m_blk = tile / num_n, n_blk = tile % num_n;
                 const int sub = g % NBUF_PER_TILE;
-                c0 = n_blk * BN + h * (BN / 2) + sub * (EPI == EPI_BIAS_RES_F32 ? 32 : 64);
+                c0 = n_blk * BN + h * (BN / 2) + sub * (EPI == EPI_BIAS_RES_SPLIT ? 32 : 64);
                 c1 = m_blk * (2 * BM) + cta_rank * BM;
             };
             auto fill = [&](int g) {  // make buffer g&1 ready for the compute threads
                 const int b = g & 1;
-                if constexpr (EPI == EPI_BIAS_RES_F32) {
+                if constexpr (EPI == EPI_BIAS_RES_SPLIT) {
                     int c0, c1;
                     coords(g, c0, c1);
                     mbar_arrive_expect_tx(&rfull[h * 2 + b], EBUF_BYTES);
-                    tma_load_2d(ebuf + b * EBUF_BYTES, &tma_out, &rfull[h * 2 + b], c0, c1);  // pre-LN residual, in place
+                    tma_load_2d(ebuf + b * EBUF_BYTES, &tma_out, &rfull[h * 2 + b], c0, c1);                  // hi chunk
+                    tma_load_2d(ebuf + b * EBUF_BYTES + EBUF_BYTES / 2, &tma_lo, &rfull[h * 2 + b], c0, c1);  // lo chunk
                 } else {
                     mbar_arrive(&rfull[h * 2 + b]);  // nothing to load: just "buffer is free"
                 }
@@ -214,6 +220,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                 int c0, c1;
                 coords(g, c0, c1);
                 tma_store_2d(&tma_out, ebuf + b * EBUF_BYTES, c0, c1);
+                if constexpr (EPI == EPI_BIAS_RES_SPLIT) tma_store_2d(&tma_lo, ebuf + b * EBUF_BYTES + EBUF_BYTES / 2, c0, c1);
                 tma_store_commit();
                 if (g + 2 < total) {
                     tma_store_wait_read<0>();  // the store has finished reading buffer b
@@ -228,44 +235,53 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int h = (warp - 4) >> 2;   // which 128 columns of the tile
         const int r = ew * 32 + lane;    // row within the CTA's 128 rows == index within the half
         const uint32_t ebuf = smem_u32(smem + OFF_EBUF + h * (2 * EBUF_BYTES));
-        const uint32_t swz = static_cast<uint32_t>(r & 7);
+        const uint32_t swz = static_cast<uint32_t>(r & 7);          // 128B swizzle: 16-byte chunk ^= row & 7
+        const uint32_t swz64 = static_cast<uint32_t>((r >> 1) & 3);  // 64B swizzle (64-byte rows): chunk ^= (row >> 1) & 3
         int as = 0;
         uint32_t aphase = 0;
         uint32_t g = 0;  // staging-buffer use counter of this half
         int tpar = 0;
         for (int tile = pair; tile < num_tiles; tile += num_pairs, tpar ^= 1) {
             const int n_blk = tile % num_n;
-            // stage this tile's bias slice (128 floats per half) once; double buffered across tiles
-            const uint32_t sb = smem_u32(sbias + tpar * 768 + h * 128);  // bias; gamma at +256 floats, beta at +512
-            sts32f(sb + r * 4, __ldg(bias + n_blk * BN + h * (BN / 2) + r));
+            const int grow = (tile / num_n) * (2 * BM) + cta_rank * BM + r;  // this thread's global row
+            // stage this tile's per-column vectors (128 floats per half) once; double buffered across tiles
+            const uint32_t sb = smem_u32(sbias + tpar * 768 + h * 128);  // bias; wsum|gamma at +256 floats, beta at +512
+            const int col = n_blk * BN + h * (BN / 2) + r;
+            sts32f(sb + r * 4, __ldg(bias + col));
+            // statistics of the LayerNorm this epilogue folds (EPI 0/1) or re-applies to the residual (EPI 2)
             float ln_mean = 0.f, ln_rstd = 1.f;
-            if constexpr (EPI == EPI_BIAS_RES_F32) {
-                const bool has_ln = ln_stats != nullptr;
-                sts32f(sb + 1024 + r * 4, has_ln ? __ldg(ln_gamma + n_blk * BN + h * (BN / 2) + r) : 1.0f);
-                sts32f(sb + 2048 + r * 4, has_ln ? __ldg(ln_beta + n_blk * BN + h * (BN / 2) + r) : 0.0f);
-                if (has_ln) {
-                    const int grow = (tile / num_n) * (2 * BM) + cta_rank * BM + r;
-                    const float2 st = __ldg(ln_stats + grow);  // (mean, rstd) of this thread's row
-                    ln_mean = st.x;
-                    ln_rstd = st.y;
+            const bool has_ln = ep.stats_in != nullptr;
+            if (has_ln) {
+                const float2* __restrict__ pp = ep.stats_in + static_cast<size_t>(grow) * ep.parts_in;
+                float sum = 0.f;
+                for (int j = 0; j < ep.parts_in; ++j) sum += __ldg(&pp[j].x);
+                const float inv_n = 1.0f / (128.0f * ep.parts_in);
+                ln_mean = sum * inv_n;
+                float m2 = 0.f;
+                for (int j = 0; j < ep.parts_in; ++j) {
+                    const float2 pj = __ldg(&pp[j]);
+                    const float d = pj.x * (1.0f / 128.0f) - ln_mean;
+                    m2 += fmaf(128.0f * d, d, pj.y);
                 }
+                ln_rstd = rsqrtf(m2 * inv_n + ep.eps);
+            }
+            if constexpr (EPI == EPI_BIAS_RES_SPLIT) {
+                sts32f(sb + 1024 + r * 4, has_ln ? __ldg(ep.ln_gamma + col) : 1.0f);
+                sts32f(sb + 2048 + r * 4, has_ln ? __ldg(ep.ln_beta + col) : 0.0f);
             }
             named_bar_sync(1 + h, 128);
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
+            // running statistics of this thread's 128 new values (EPI 2): count 32 c, mean, M2
+            float run_mean = 0.f, run_m2 = 0.f;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t acc[32];
                 tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BN + h * (BN / 2) + c * 32, acc);
-                float bv[32];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 b4 = lds128f(sb + (c * 32 + 4 * j) * 4);  // broadcast read
-                    bv[4 * j] = b4.x; bv[4 * j + 1] = b4.y; bv[4 * j + 2] = b4.z; bv[4 * j + 3] = b4.w;
-                }
                 const uint32_t b = g & 1;
-                const uint32_t row_ptr = ebuf + b * EBUF_BYTES + r * 128;
-                if constexpr (EPI == EPI_BIAS_RES_F32) {
+                if constexpr (EPI == EPI_BIAS_RES_SPLIT) {
+                    const uint32_t row_hi = ebuf + b * EBUF_BYTES + r * 64;
+                    const uint32_t row_lo = row_hi + EBUF_BYTES / 2;
                     mbar_wait(&rfull[h * 2 + b], (g >> 1) & 1);  // residual chunk has landed
                     tmem_ld_wait();
                     if (c == 3) {  // last TMEM read of this tile: release the accumulator to the MMA warp early
@@ -273,22 +289,63 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(&tempty[as], 0);
                     }
+                    float v[32];
+                    float csum = 0.f;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t p = row_ptr + ((static_cast<uint32_t>(q) ^ swz) << 4);
-                        const float4 y = lds128f(p);  // pre-LN residual
-                        const float4 gm = lds128f(sb + 1024 + (c * 32 + 4 * q) * 4);
-                        const float4 bt = lds128f(sb + 2048 + (c * 32 + 4 * q) * 4);
-                        // LN(y) with exactly ln_kernel's operations: fmaf((y - mean) * rstd, gamma, beta)
-                        const float r0 = fmaf((y.x - ln_mean) * ln_rstd, gm.x, bt.x), r1 = fmaf((y.y - ln_mean) * ln_rstd, gm.y, bt.y);
-                        const float r2 = fmaf((y.z - ln_mean) * ln_rstd, gm.z, bt.z), r3 = fmaf((y.w - ln_mean) * ln_rstd, gm.w, bt.w);
-                        sts128f(p, __uint_as_float(acc[4 * q]) + bv[4 * q] + r0, __uint_as_float(acc[4 * q + 1]) + bv[4 * q + 1] + r1,
-                                __uint_as_float(acc[4 * q + 2]) + bv[4 * q + 2] + r2, __uint_as_float(acc[4 * q + 3]) + bv[4 * q + 3] + r3);
+                    for (int q = 0; q < 4; ++q) {  // 8 columns per 16-byte chunk of hi / lo
+                        const uint32_t off = (static_cast<uint32_t>(q) ^ swz64) << 4;
+                        uint32_t hh[4], ll[4];
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hh[0]), "=r"(hh[1]), "=r"(hh[2]), "=r"(hh[3]) : "r"(row_hi + off) : "memory");
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(ll[0]), "=r"(ll[1]), "=r"(ll[2]), "=r"(ll[3]) : "r"(row_lo + off) : "memory");
+#pragma unroll
+                        for (int e2 = 0; e2 < 2; ++e2) {  // 4 columns at a time (one float4 of each per-column vector)
+                            const int cc = c * 32 + q * 8 + e2 * 4;
+                            const float4 bv = lds128f(sb + cc * 4);
+                            const float4 gm = lds128f(sb + 1024 + cc * 4);
+                            const float4 bt = lds128f(sb + 2048 + cc * 4);
+                            const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&hh[e2 * 2]));
+                            const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&hh[e2 * 2 + 1]));
+                            const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&ll[e2 * 2]));
+                            const float2 l1 = __half22float2(*reinterpret_cast<const __half2*>(&ll[e2 * 2 + 1]));
+                            const float y0 = h0.x + l0.x, y1 = h0.y + l0.y, y2 = h1.x + l1.x, y3 = h1.y + l1.y;
+                            // LN(y) = fmaf((y - mean) * rstd, gamma, beta); new value = acc + bias + LN(y)
+                            const int i = q * 8 + e2 * 4;
+                            v[i] = __uint_as_float(acc[i]) + bv.x + fmaf((y0 - ln_mean) * ln_rstd, gm.x, bt.x);
+                            v[i + 1] = __uint_as_float(acc[i + 1]) + bv.y + fmaf((y1 - ln_mean) * ln_rstd, gm.y, bt.y);
+                            v[i + 2] = __uint_as_float(acc[i + 2]) + bv.z + fmaf((y2 - ln_mean) * ln_rstd, gm.z, bt.z);
+                            v[i + 3] = __uint_as_float(acc[i + 3]) + bv.w + fmaf((y3 - ln_mean) * ln_rstd, gm.w, bt.w);
+                            csum += (v[i] + v[i + 1]) + (v[i + 2] + v[i + 3]);
+                        }
+                        // split v = hi' + lo' and write both back in place
+                        uint32_t nh[4], nl[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float a0 = v[q * 8 + 2 * e], a1 = v[q * 8 + 2 * e + 1];
+                            const __half2 hp = __floats2half2_rn(a0, a1);
+                            const float2 hb = __half22float2(hp);
+                            nh[e] = *reinterpret_cast<const uint32_t*>(&hp);
+                            nl[e] = pack_half2(a0 - hb.x, a1 - hb.y);
+                        }
+                        sts128(row_hi + off, nh[0], nh[1], nh[2], nh[3]);
+                        sts128(row_lo + off, nl[0], nl[1], nl[2], nl[3]);
                     }
                     fence_proxy_async_smem();
                     mbar_arrive(&cdone[h * 2 + b]);
                     ++g;
+                    // merge this chunk's (mean, M2) into the running statistics (Chan et al.)
+                    const float cmean = csum * (1.0f / 32.0f);
+                    float cm2 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const float d = v[i] - cmean;
+                        cm2 = fmaf(d, d, cm2);
+                    }
+                    const float n_run = 32.0f * c, n_new = n_run + 32.0f;
+                    const float delta = cmean - run_mean;
+                    run_mean += delta * (32.0f / n_new);
+                    run_m2 += cm2 + delta * delta * (n_run * 32.0f / n_new);
                 } else {
+                    const uint32_t row_ptr = ebuf + b * EBUF_BYTES + r * 128;
                     if ((c & 1) == 0) mbar_wait(&rfull[h * 2 + b], (g >> 1) & 1);  // buffer is free
                     tmem_ld_wait();
                     if (c == 3) {
@@ -298,9 +355,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     }
                     float v[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = __uint_as_float(acc[j]) + bv[j];
-                        if constexpr (EPI == EPI_BIAS_GELU_F16) v[j] = gelu_erf(v[j]);
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b4 = lds128f(sb + (c * 32 + 4 * j) * 4);  // bias (or W beta + b): broadcast read
+                        // folded LayerNorm: rstd * acc + c -- the weight rows are centred at load time (sum_k W''[n,k] = 0), so
+                        // the row mean cancels inside the tensor core: sum_k (y_k - mean) W''_nk = sum_k y_k W''_nk
+                        v[4 * j] = fmaf(ln_rstd, __uint_as_float(acc[4 * j]), b4.x);
+                        v[4 * j + 1] = fmaf(ln_rstd, __uint_as_float(acc[4 * j + 1]), b4.y);
+                        v[4 * j + 2] = fmaf(ln_rstd, __uint_as_float(acc[4 * j + 2]), b4.z);
+                        v[4 * j + 3] = fmaf(ln_rstd, __uint_as_float(acc[4 * j + 3]), b4.w);
+                    }
+                    if constexpr (EPI == EPI_BIAS_GELU_F16) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -314,6 +380,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                         ++g;
                     }
                 }
+            }
+            if constexpr (EPI == EPI_BIAS_RES_SPLIT) {
+                // this thread's 128 columns of the new row: one (sum, M2) partial
+                if (ep.stats_out != nullptr)
+                    ep.stats_out[static_cast<size_t>(grow) * (N / 128) + n_blk * 2 + h] = make_float2(run_mean * 128.0f, run_m2);
             }
             as ^= 1;
             if (as == 0) aphase ^= 1;
@@ -333,12 +404,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 }  // namespace gemm
 
 template <int EPI>
-static cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const LnRef& ln,
-                               const float* bias, int M, int N, int K, int sm_count, cudaStream_t stream, int dbg_mode) {
+static cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& tlo,
+                               const GemmEpi& e, int M, int N, int K, int sm_count, cudaStream_t stream, int dbg_mode) {
     const int tiles = ((M + 2 * gemm::BM - 1) / (2 * gemm::BM)) * (N / gemm::BN);
     int pairs = sm_count / 2;
     if (tiles < pairs) pairs = tiles;
-    gemm::gemm_pair_kernel<EPI><<<2 * pairs, gemm::NUM_THREADS, gemm::SMEM_BYTES, stream>>>(ta, tb, tout, bias, ln.stats, ln.gamma, ln.beta, M, N, K, dbg_mode);
+    gemm::gemm_pair_kernel<EPI><<<2 * pairs, gemm::NUM_THREADS, gemm::SMEM_BYTES, stream>>>(ta, tb, tout, tlo, e, M, N, K, dbg_mode);
     return cudaGetLastError();
 }
 
@@ -348,22 +419,25 @@ cudaError_t gemm_init_device() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm::gemm_pair_kernel<EPI_BIAS_GELU_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(gemm::gemm_pair_kernel<EPI_BIAS_RES_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES);
+    return cudaFuncSetAttribute(gemm::gemm_pair_kernel<EPI_BIAS_RES_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES);
 }
 
-// Bits 8+ of `epi` select a diagnostic mode (low nibble: 1 = no TMA loads, 2 = no MMA; high nibble: ring
-// length) used only by tools/gemm_diag.py.
-cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const LnRef* ln,
-                        const float* bias, int M, int N, int K, int sm_count, cudaStream_t stream) {
+// Bits 8+ of `epi` select a diagnostic mode in B200RT_DIAG builds (tools/gemm_diag.py); they are ignored otherwise.
+cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap* tlo,
+                        const GemmEpi& e, int M, int N, int K, int sm_count, cudaStream_t stream) {
     const int dbg_mode = epi >> 8;
     epi &= 0xFF;
-    if (N % gemm::BN != 0 || K % gemm::BK != 0 || M <= 0) return cudaErrorInvalidValue;
-    const LnRef none{nullptr, nullptr, nullptr};
-    const LnRef& l = ln ? *ln : none;
+    if (N % gemm::BN != 0 || K % gemm::BK != 0 || M <= 0 || e.bias == nullptr) return cudaErrorInvalidValue;
+    if (e.stats_in != nullptr && (e.parts_in < 1 || e.parts_in > 32)) return cudaErrorInvalidValue;
     switch (epi) {
-        case EPI_BIAS_F16: return launch_pair<EPI_BIAS_F16>(ta, tb, tout, l, bias, M, N, K, sm_count, stream, dbg_mode);
-        case EPI_BIAS_GELU_F16: return launch_pair<EPI_BIAS_GELU_F16>(ta, tb, tout, l, bias, M, N, K, sm_count, stream, dbg_mode);
-        case EPI_BIAS_RES_F32: return launch_pair<EPI_BIAS_RES_F32>(ta, tb, tout, l, bias, M, N, K, sm_count, stream, dbg_mode);
+        case EPI_BIAS_F16:
+        case EPI_BIAS_GELU_F16:
+            return epi == EPI_BIAS_F16 ? launch_pair<EPI_BIAS_F16>(ta, tb, tout, tout, e, M, N, K, sm_count, stream, dbg_mode)
+                                       : launch_pair<EPI_BIAS_GELU_F16>(ta, tb, tout, tout, e, M, N, K, sm_count, stream, dbg_mode);
+        case EPI_BIAS_RES_SPLIT:
+            if (tlo == nullptr || (e.stats_in != nullptr && (e.ln_gamma == nullptr || e.ln_beta == nullptr))) return cudaErrorInvalidValue;
+            if (e.stats_out != nullptr && e.stats_out == e.stats_in) return cudaErrorInvalidValue;
+            return launch_pair<EPI_BIAS_RES_SPLIT>(ta, tb, tout, *tlo, e, M, N, K, sm_count, stream, dbg_mode);
     }
     return cudaErrorInvalidValue;
 }

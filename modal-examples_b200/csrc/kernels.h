@@ -8,34 +8,52 @@
 namespace b200 {
 
 enum GemmEpilogue : int {
-    EPI_BIAS_F16 = 0,       // out fp16 = acc + bias                      (fused QKV projection)
-    EPI_BIAS_GELU_F16 = 1,  // out fp16 = gelu_erf(acc + bias)            (FFN up-projection)
-    EPI_BIAS_RES_F32 = 2,   // y fp32 (in place) = acc + bias + LN(y)     (attention-out / FFN down); LN(y) =
-                            //   (y - mean) * rstd * gamma + beta from the row statistics of the previous LayerNorm
+    EPI_BIAS_F16 = 0,       // out fp16 = LNfold(acc) + bias                     (fused QKV projection)
+    EPI_BIAS_GELU_F16 = 1,  // out fp16 = gelu_erf(LNfold(acc) + bias)           (FFN up-projection)
+    EPI_BIAS_RES_SPLIT = 2, // y (fp16 hi + fp16 lo, in place) = acc + bias + LN(y)  (attention-out / FFN down) + row statistics
 };
 
 constexpr int HIDDEN = 768;
 constexpr int HEADS = 12;
 constexpr int HEAD_DIM = 64;
 constexpr int QKV_DIM = 3 * HIDDEN;
+constexpr int STAT_PARTS = HIDDEN / 128;  // row statistics travel as one (sum, M2) partial per 128 columns
 
 // One-time per-device setup (dynamic shared memory opt-in for every kernel). Call with the device current.
 cudaError_t kernels_init_device();
 
-// C[M,N] = epi(A[M,K] . W[N,K]^T + bias) on CTA pairs.  All operands move by TMA (128B swizzle):
-//   ta  : fp16 A   {K, rows>=M}  box {64,128}        tb  : fp16 W {K, N} box {64,128}
-//   tout: fp16 out {N, rows} box {64,128} (EPI 0/1)  or  fp32 out {N, rows} box {32,128} (EPI 2)
-//   EPI 2 reads the pre-LN residual through the same map `tout` (in place) and needs `ln`: the statistics and
-//         affine of the LayerNorm that produced this GEMM's residual input (NULL for EPI 0/1).  With ln.stats ==
-//         NULL the residual is added as is (plain `out += acc + bias`, used by the kernel-level tests).
+// The residual stream lives in HBM as y = hi + lo (two fp16 arrays, 22 mantissa bits together), stored PRE-LayerNorm, with
+// the row statistics of the LayerNorm that applies to it as STAT_PARTS partials per row: (sum, M2 about the partial's own
+// mean) over each 128-column slice, written by whoever produced the row (embedding kernel or a residual GEMM epilogue).
+// No kernel ever materialises LN(y):
+//   * a GEMM that consumes LN(y) reads `hi` as its fp16 A operand against W'' = fp16(gamma o W - rowmean(gamma o W)): gamma folded
+//     into the weight's columns and every row centred at load time, so that sum_k (y_k - mean) W''_nk = sum_k y_k W''_nk and the
+//     row mean never has to be subtracted; its epilogue applies  rstd * acc + (W beta + b)   -- "LNfold";
+//   * a GEMM that adds the residual LN(y) re-applies (y - mean) * rstd * gamma + beta in its epilogue.
+//
+// C[M,N] = epi(A[M,K] . W[N,K]^T) on CTA pairs.  All operands move by TMA:
+//   ta  : fp16 A   {K, rows>=M}  box {64,128} SW128     tb  : fp16 W {K, N} box {64,128} SW128
+//   EPI 0/1: tout = fp16 out {N, rows} box {64,128} SW128; e.stats_in (or NULL: plain acc + bias), e.bias
+//   EPI 2  : tout = hi, tlo = lo, both fp16 {N, rows} box {32,128} SW64 (read and written in place); e.stats_in + e.ln_gamma/
+//            e.ln_beta describe the LayerNorm of the residual (stats_in NULL: the residual is added as is); e.stats_out
+//            receives the partials of the new rows (N / 128 per row; must not alias stats_in: other tiles still read those).
 //   N % 256 == 0, K % 64 == 0; rows past M are clipped by the maps' own bounds.
-struct LnRef {
-    const float2* stats;  // [rows] (mean, rstd)
-    const float* gamma;   // [N]
-    const float* beta;    // [N]
+struct GemmEpi {
+    const float* bias;        // [N]
+    const float2* stats_in;   // [rows][parts_in]
+    int parts_in;             // partials per row of stats_in (LayerNorm width / 128)
+    const float* ln_gamma;    // [N] EPI 2
+    const float* ln_beta;     // [N] EPI 2
+    float2* stats_out;        // [rows][N / 128] EPI 2 (may be NULL)
+    float eps;
 };
-cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const LnRef* ln,
-                        const float* bias, int M, int N, int K, int sm_count, cudaStream_t stream);
+cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap* tlo,
+                        const GemmEpi& e, int M, int N, int K, int sm_count, cudaStream_t stream);
+
+// gamma != NULL: w_out[n,k] = fp16(w[n,k] gamma[k] - mean_k(w[n,:] gamma)), cvec[n] = sum_k w[n,k] beta[k] + bias[n]
+// gamma == NULL: w_out = fp16(w) (cvec untouched)
+cudaError_t launch_fold_ln(const float* w, const float* gamma, const float* beta, const float* bias, __half* w_out, float* cvec,
+                           int N, int K, cudaStream_t stream);
 
 // Multi-head self-attention over a padded batch: qkv fp16 [B, S, 2304] (Q | K | V, head-major within each),
 // lens[B] valid keys per item, ctx fp16 [B*S, 768].  tq: 3D map over qkv {2304, S, B}, tctx: 3D map over ctx {768, S, B};
@@ -44,20 +62,18 @@ cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
 cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tctx, const int32_t* lens, int B, int S,
                              cudaStream_t stream, unsigned long long* dbg = nullptr);
 
-// word + position + token_type(0) embedding gather -> y32 (fp32 pre-LN sum = residual stream), LayerNorm ->
-// x16 (GEMM operand) + stats (mean, rstd per row).  x32_dbg (tests only, else NULL): normalised fp32 rows.
-cudaError_t launch_embed_ln(const int32_t* ids, const float* word, const float* pos, const float* type0,
-                            const float* gamma, const float* beta, float* y32, __half* x16, float2* stats, float* x32_dbg,
-                            int n_tokens, int S, int vocab, float eps, cudaStream_t stream);
+// word + position + token_type(0) embedding gather -> y = hi + lo (pre-LN residual stream) + the row's statistic partials.
+cudaError_t launch_embed(const int32_t* ids, const float* word, const float* pos, const float* type0, __half* yhi, __half* ylo,
+                         float2* stats, int n_tokens, int S, int vocab, cudaStream_t stream);
 
-// LayerNorm over rows of y (fp32 pre-LN sum) -> x16 + stats; x32_dbg as above
-cudaError_t launch_ln(const float* y, const float* gamma, const float* beta, __half* x16, float2* stats, float* x32_dbg,
-                      int n_rows, float eps, cudaStream_t stream);
+// debug only: x32[row] = LN(hi + lo) with the row's own statistics (the product path never materialises this)
+cudaError_t launch_ln_materialize(const __half* yhi, const __half* ylo, const float* gamma, const float* beta, float* x32,
+                                  int n_rows, float eps, cudaStream_t stream);
 
-// final LayerNorm of the CLS row of every item + L2 normalise; row i is stored at out + (out_row0 + i) * 768,
+// final LayerNorm of the CLS row of every item + L2 normalise; row i is stored at out + i * 768,
 // where `out` may be a peer-mapped pointer into the root GPU's gather buffer (the fused gather).
-cudaError_t launch_pool_normalize(const float* y, const float* gamma, const float* beta, float* out, int n_items,
-                                  int S, float eps, cudaStream_t stream);
+cudaError_t launch_pool_normalize(const __half* yhi, const __half* ylo, const float* gamma, const float* beta, float* out,
+                                  int n_items, int S, float eps, cudaStream_t stream);
 
 // fp32 -> fp16 (weight conversion at model load)
 cudaError_t launch_f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t stream);

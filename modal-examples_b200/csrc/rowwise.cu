@@ -1,14 +1,13 @@
-// HBM-bound row-wise kernels (sm_100a): embedding gather + LayerNorm, LayerNorm, CLS pooling +
-// final LayerNorm + L2 normalise with the store aimed at the root GPU's gather buffer, the root-side
-// scatter of token ids into (peer) shard inputs, and the fp32 -> fp16 weight conversion.
+// HBM-bound row-wise kernels (sm_100a): embedding gather into the split residual stream, CLS pooling + final LayerNorm +
+// L2 normalise with the store aimed at the root GPU's gather buffer, the root-side scatter of token ids into (peer) shard
+// inputs, the load-time weight preparation (fp32 -> fp16, LayerNorm gamma folded into weight columns), and a debug-only
+// LayerNorm materialisation.
 //
-// All of them: one warp per 768-wide row, 128-bit loads/stores (6 float4 per lane), statistics by
-// warp shuffle in fp32, two-pass variance on register-resident data (no E[x^2]-E[x]^2 cancellation).
+// Row kernels: one warp per 768-wide row, 128-bit accesses, statistics by warp shuffle in fp32, two-pass variance on
+// register-resident data (no E[x^2]-E[x]^2 cancellation).
 //
-// The fp32 residual stream is stored PRE-LayerNorm (y32) together with per-row (mean, rstd): the LayerNorm
-// kernels write only the fp16 GEMM operand (x16) and the statistics (4.5 KB/row of traffic instead of 7.5),
-// and the next residual-adding GEMM epilogue re-applies (y - mean) * rstd * gamma + beta with the very same
-// fp32 operations, so the normalised fp32 row is bit-identical to the one a materialising kernel would write.
+// The residual stream is stored PRE-LayerNorm as y = hi + lo (fp16 + fp16) together with STAT_PARTS (sum, M2) partials per
+// row; there is no LayerNorm kernel in the product path -- the consuming GEMM folds it into its epilogue (kernels.h).
 //
 // Restates BertEmbeddings.forward (HF modeling_bert.py:72-111), the LayerNorm halves of
 // BertSelfOutput :287-298 / BertOutput :345-356, and sentence-transformers' CLS pooling + Normalize
@@ -20,8 +19,9 @@ namespace b200 {
 namespace rw {
 
 constexpr int H = HIDDEN;          // 768
-constexpr int V4 = H / 4 / 32;     // float4 per lane = 6
+constexpr int V4 = H / 4 / 32;     // float4 per lane = 6: float4 i of lane l holds columns [128 i + 4 l, +4)
 constexpr int WARPS_PER_BLOCK = 8;
+static_assert(V4 == STAT_PARTS, "float4 i of every lane covers exactly the i-th 128-column slice");
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -57,24 +57,24 @@ __device__ __forceinline__ float2 ln_inplace(float4 (&x)[V4], const float* __res
     return make_float2(mean, rstd);
 }
 
-// fp16 copy of the normalised row (the GEMM operand); x32 only for the debug materialisation
-__device__ __forceinline__ void store_row(const float4 (&x)[V4], float* __restrict__ x32, __half* __restrict__ x16,
-                                          size_t row, int lane) {
-    uint2* o16 = reinterpret_cast<uint2*>(x16 + row * H);
+// y = hi + lo of one row -> 24 fp32 values per lane (same column mapping as a float4 row)
+__device__ __forceinline__ void load_split_row(const __half* __restrict__ yhi, const __half* __restrict__ ylo, size_t row, int lane,
+                                               float4 (&x)[V4]) {
+    const uint2* h2 = reinterpret_cast<const uint2*>(yhi + row * H);
+    const uint2* l2 = reinterpret_cast<const uint2*>(ylo + row * H);
 #pragma unroll
-    for (int i = 0; i < V4; ++i) o16[i * 32 + lane] = make_uint2(pack_half2(x[i].x, x[i].y), pack_half2(x[i].z, x[i].w));
-    if (x32 != nullptr) {
-        float4* o32 = reinterpret_cast<float4*>(x32 + row * H);
-#pragma unroll
-        for (int i = 0; i < V4; ++i) o32[i * 32 + lane] = x[i];
+    for (int i = 0; i < V4; ++i) {
+        const uint2 hv = h2[i * 32 + lane], lv = l2[i * 32 + lane];
+        const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&hv.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
+        const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&lv.x)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&lv.y));
+        x[i] = make_float4(h0.x + l0.x, h0.y + l0.y, h1.x + l1.x, h1.y + l1.y);
     }
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-embed_ln_kernel(const int32_t* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ pos,
-                const float* __restrict__ type0, const float* __restrict__ gamma, const float* __restrict__ beta,
-                float* __restrict__ y32, __half* __restrict__ x16, float2* __restrict__ stats, float* __restrict__ x32_dbg,
-                int n_tokens, int S, int vocab, float eps) {
+embed_kernel(const int32_t* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ pos,
+             const float* __restrict__ type0, __half* __restrict__ yhi, __half* __restrict__ ylo, float2* __restrict__ stats,
+             int n_tokens, int S, int vocab) {
     const int lane = threadIdx.x & 31;
     const int tok = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (tok >= n_tokens) return;
@@ -84,49 +84,54 @@ embed_ln_kernel(const int32_t* __restrict__ ids, const float* __restrict__ word,
     const float4* w4 = reinterpret_cast<const float4*>(word + static_cast<size_t>(id) * H);
     const float4* p4 = reinterpret_cast<const float4*>(pos + static_cast<size_t>(p) * H);
     const float4* t4 = reinterpret_cast<const float4*>(type0);
-    float4 x[V4];
+    uint2* oh = reinterpret_cast<uint2*>(yhi + static_cast<size_t>(tok) * H);
+    uint2* ol = reinterpret_cast<uint2*>(ylo + static_cast<size_t>(tok) * H);
+    float ps = 0.f, pq = 0.f;  // lane i < STAT_PARTS keeps partial i
 #pragma unroll
     for (int i = 0; i < V4; ++i) {
         const float4 a = __ldg(w4 + i * 32 + lane);
         const float4 b = __ldg(p4 + i * 32 + lane);
         const float4 c = __ldg(t4 + i * 32 + lane);
         // HF order: (word + token_type) + position
-        x[i] = make_float4((a.x + c.x) + b.x, (a.y + c.y) + b.y, (a.z + c.z) + b.z, (a.w + c.w) + b.w);
+        const float4 x = make_float4((a.x + c.x) + b.x, (a.y + c.y) + b.y, (a.z + c.z) + b.z, (a.w + c.w) + b.w);
+        // the residual stream is kept PRE-LayerNorm as hi + lo; consumers fold / re-apply the LayerNorm
+        const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        oh[i * 32 + lane] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        ol[i * 32 + lane] = make_uint2(pack_half2(x.x - f0.x, x.y - f0.y), pack_half2(x.z - f1.x, x.w - f1.y));
+        // (sum, M2 about its own mean) of this 128-column slice: float4 i of the 32 lanes is exactly slice i
+        const float s = warp_sum((x.x + x.y) + (x.z + x.w));
+        const float m = s * (1.0f / 128.0f);
+        const float dx = x.x - m, dy = x.y - m, dz = x.z - m, dw = x.w - m;
+        const float q = warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw));
+        if (lane == i) { ps = s; pq = q; }
     }
-    // the residual stream is kept PRE-LayerNorm (y32) plus per-row (mean, rstd); consumers re-apply the affine
-    float4* y4 = reinterpret_cast<float4*>(y32 + static_cast<size_t>(tok) * H);
-#pragma unroll
-    for (int i = 0; i < V4; ++i) y4[i * 32 + lane] = x[i];
-    const float2 st = ln_inplace(x, gamma, beta, eps, lane);
-    if (lane == 0) stats[tok] = st;
-    store_row(x, x32_dbg, x16, tok, lane);
+    if (lane < STAT_PARTS) stats[static_cast<size_t>(tok) * STAT_PARTS + lane] = make_float2(ps, pq);
 }
 
+// debug only (b200rt_debug_hidden): materialise LN(hi + lo) in fp32
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-ln_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
-          __half* __restrict__ x16, float2* __restrict__ stats, float* __restrict__ x32_dbg, int n_rows, float eps) {
+ln_materialize_kernel(const __half* __restrict__ yhi, const __half* __restrict__ ylo, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float* __restrict__ x32, int n_rows, float eps) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (row >= n_rows) return;
-    const float4* y4 = reinterpret_cast<const float4*>(y + static_cast<size_t>(row) * H);
     float4 x[V4];
+    load_split_row(yhi, ylo, row, lane, x);
+    ln_inplace(x, gamma, beta, eps, lane);
+    float4* o32 = reinterpret_cast<float4*>(x32 + static_cast<size_t>(row) * H);
 #pragma unroll
-    for (int i = 0; i < V4; ++i) x[i] = y4[i * 32 + lane];
-    const float2 st = ln_inplace(x, gamma, beta, eps, lane);
-    if (lane == 0) stats[row] = st;
-    store_row(x, x32_dbg, x16, row, lane);
+    for (int i = 0; i < V4; ++i) o32[i * 32 + lane] = x[i];
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
-pool_normalize_kernel(const float* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      float* __restrict__ out, int n_items, int S, float eps) {
+pool_normalize_kernel(const __half* __restrict__ yhi, const __half* __restrict__ ylo, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, float* __restrict__ out, int n_items, int S, float eps) {
     const int lane = threadIdx.x & 31;
     const int item = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     if (item >= n_items) return;
-    const float4* y4 = reinterpret_cast<const float4*>(y + static_cast<size_t>(item) * S * H);  // CLS row
     float4 x[V4];
-#pragma unroll
-    for (int i = 0; i < V4; ++i) x[i] = y4[i * 32 + lane];
+    load_split_row(yhi, ylo, static_cast<size_t>(item) * S, lane, x);  // CLS row
     ln_inplace(x, gamma, beta, eps, lane);
     float q = 0.f;
 #pragma unroll
@@ -136,6 +141,37 @@ pool_normalize_kernel(const float* __restrict__ y, const float* __restrict__ gam
 #pragma unroll
     for (int i = 0; i < V4; ++i)
         o4[i * 32 + lane] = make_float4(x[i].x * inv, x[i].y * inv, x[i].z * inv, x[i].w * inv);
+}
+
+// Load-time weight preparation, one warp per output row n of W[N,K] (see kernels.h, "LNfold"):
+//   gamma given: w_out[n,k] = fp16(w[n,k] gamma[k] - m_n),  m_n = mean_k(w[n,k] gamma[k])   (rows centred: the LayerNorm's mean
+//                subtraction then happens inside the GEMM),  cvec[n] = sum_k w[n,k] beta[k] + bias[n]
+//   gamma NULL : w_out[n,k] = fp16(w[n,k])
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+fold_ln_kernel(const float* __restrict__ w, const float* __restrict__ gamma, const float* __restrict__ beta,
+               const float* __restrict__ bias, __half* __restrict__ w_out, float* __restrict__ cvec, int N, int K) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const float* wr = w + static_cast<size_t>(n) * K;
+    __half* orow = w_out + static_cast<size_t>(n) * K;
+    float m = 0.f;
+    if (gamma != nullptr) {
+        float s = 0.f, c = 0.f;
+        for (int k = lane * 2; k < K; k += 64) {
+            const float2 wv = *reinterpret_cast<const float2*>(wr + k);
+            s += fmaf(wv.x, __ldg(gamma + k), wv.y * __ldg(gamma + k + 1));
+            c = fmaf(wv.x, __ldg(beta + k), fmaf(wv.y, __ldg(beta + k + 1), c));
+        }
+        m = warp_sum(s) / static_cast<float>(K);
+        c = warp_sum(c);
+        if (lane == 0 && cvec != nullptr) cvec[n] = c + (bias != nullptr ? bias[n] : 0.f);
+    }
+    for (int k = lane * 2; k < K; k += 64) {
+        const float2 wv = *reinterpret_cast<const float2*>(wr + k);
+        const float g0 = gamma != nullptr ? __ldg(gamma + k) : 1.f, g1 = gamma != nullptr ? __ldg(gamma + k + 1) : 1.f;
+        *reinterpret_cast<__half2*>(orow + k) = __floats2half2_rn(fmaf(wv.x, g0, -m), fmaf(wv.y, g1, -m));
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -172,26 +208,32 @@ scatter_kernel(const int32_t* __restrict__ src_ids, const int32_t* __restrict__ 
 
 }  // namespace rw
 
-cudaError_t launch_embed_ln(const int32_t* ids, const float* word, const float* pos, const float* type0,
-                            const float* gamma, const float* beta, float* y32, __half* x16, float2* stats, float* x32_dbg,
-                            int n_tokens, int S, int vocab, float eps, cudaStream_t stream) {
+cudaError_t launch_embed(const int32_t* ids, const float* word, const float* pos, const float* type0, __half* yhi, __half* ylo,
+                         float2* stats, int n_tokens, int S, int vocab, cudaStream_t stream) {
     const int grid = (n_tokens + rw::WARPS_PER_BLOCK - 1) / rw::WARPS_PER_BLOCK;
-    rw::embed_ln_kernel<<<grid, rw::WARPS_PER_BLOCK * 32, 0, stream>>>(ids, word, pos, type0, gamma, beta, y32, x16, stats,
-                                                                       x32_dbg, n_tokens, S, vocab, eps);
+    rw::embed_kernel<<<grid, rw::WARPS_PER_BLOCK * 32, 0, stream>>>(ids, word, pos, type0, yhi, ylo, stats, n_tokens, S, vocab);
     return cudaGetLastError();
 }
 
-cudaError_t launch_ln(const float* y, const float* gamma, const float* beta, __half* x16, float2* stats, float* x32_dbg,
-                      int n_rows, float eps, cudaStream_t stream) {
+cudaError_t launch_ln_materialize(const __half* yhi, const __half* ylo, const float* gamma, const float* beta, float* x32,
+                                  int n_rows, float eps, cudaStream_t stream) {
     const int grid = (n_rows + rw::WARPS_PER_BLOCK - 1) / rw::WARPS_PER_BLOCK;
-    rw::ln_kernel<<<grid, rw::WARPS_PER_BLOCK * 32, 0, stream>>>(y, gamma, beta, x16, stats, x32_dbg, n_rows, eps);
+    rw::ln_materialize_kernel<<<grid, rw::WARPS_PER_BLOCK * 32, 0, stream>>>(yhi, ylo, gamma, beta, x32, n_rows, eps);
     return cudaGetLastError();
 }
 
-cudaError_t launch_pool_normalize(const float* y, const float* gamma, const float* beta, float* out, int n_items,
-                                  int S, float eps, cudaStream_t stream) {
+cudaError_t launch_pool_normalize(const __half* yhi, const __half* ylo, const float* gamma, const float* beta, float* out,
+                                  int n_items, int S, float eps, cudaStream_t stream) {
     const int grid = (n_items + rw::WARPS_PER_BLOCK - 1) / rw::WARPS_PER_BLOCK;
-    rw::pool_normalize_kernel<<<grid, rw::WARPS_PER_BLOCK * 32, 0, stream>>>(y, gamma, beta, out, n_items, S, eps);
+    rw::pool_normalize_kernel<<<grid, rw::WARPS_PER_BLOCK * 32, 0, stream>>>(yhi, ylo, gamma, beta, out, n_items, S, eps);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fold_ln(const float* w, const float* gamma, const float* beta, const float* bias, __half* w_out, float* cvec,
+                           int N, int K, cudaStream_t stream) {
+    if (K % 64 != 0 || N < 1) return cudaErrorInvalidValue;
+    const int grid = (N + rw::WARPS_PER_BLOCK - 1) / rw::WARPS_PER_BLOCK;
+    rw::fold_ln_kernel<<<grid, rw::WARPS_PER_BLOCK * 32, 0, stream>>>(w, gamma, beta, bias, w_out, cvec, N, K);
     return cudaGetLastError();
 }
 

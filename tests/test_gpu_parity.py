@@ -68,9 +68,83 @@ def test_gemm_kernel_vs_numpy(rt, M, N, K, epi):
     resid = rng.standard_normal((M, N)).astype(np.float32) if epi == 2 else None
     out, _ = rt.debug_gemm(epi, a, w, bias, resid)
     ref = ref_gemm(a, w, bias, epi, resid)
-    # fp16 output rounding (2^-11 relative) dominates for epi 0/1; fp32 accumulation-order noise for epi 2
-    tol = (2e-3 * np.abs(ref) + 2e-3) if epi != 2 else (1e-4 * np.abs(ref) + 1e-4)
-    assert (np.abs(out.astype(np.float32) - ref) <= tol).all()
+    err = np.abs(out.astype(np.float32) - ref)
+    # epi 2: the residual stream is fp16 hi + fp16 lo (22 mantissa bits): 2^-21 relative on top of fp32 accumulation order
+    tol = 2e-3 * np.abs(ref) + 2e-3 if epi != 2 else 1e-4 * np.abs(ref) + 1e-4
+    assert (err <= tol).all(), (float(err.max()), np.argwhere(err > tol)[:4])
+
+
+def _partials(y):
+    """(sum, M2 about the slice mean) per 128-column slice: the form row statistics travel in (kernels.h)."""
+    M, W = y.shape
+    sl = y.astype(np.float64).reshape(M, W // 128, 128)
+    s = sl.sum(-1)
+    m2 = ((sl - sl.mean(-1, keepdims=True)) ** 2).sum(-1)
+    return np.stack([s, m2], -1).astype(np.float32)
+
+
+@pytest.mark.parametrize("M,N,epi", [(300, 2304, 0), (300, 3072, 1), (2 * 148 * 128 + 77, 2304, 0)])
+def test_gemm_folded_layernorm_epilogue(rt, M, N, epi):
+    """QKV / FFN1 consume the raw pre-LayerNorm residual (its fp16 hi part) against fp16(gamma o W, rows centred so that the
+    LayerNorm's mean subtraction happens inside the GEMM); the epilogue applies rstd * acc + (W beta + b).
+    Reference: LayerNorm in fp64 on the same fp16-rounded operands."""
+    K, eps = 768, 1e-12
+    rng = np.random.default_rng(M + N)
+    y = (rng.standard_normal((M, K)) * 1.7 + 0.3).astype(np.float32)
+    y[:, [77, 308]] += 40.0  # outlier channels
+    gamma = (1.0 + 0.3 * rng.standard_normal(K)).astype(np.float32)
+    beta = (0.2 * rng.standard_normal(K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) * 0.04).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    y16 = y.astype(np.float16)
+    wg = W * gamma[None, :]
+    wp = (wg - wg.mean(1, keepdims=True)).astype(np.float16)
+    cvec = (W.astype(np.float64) @ beta.astype(np.float64) + b).astype(np.float32)
+    out, _ = rt.debug_gemm(epi, y16, wp, cvec, ln_stats=_partials(y), eps=eps)
+    # what the kernel is meant to equal: LN (statistics of the fp32 row) applied to the fp16-rounded row, folded weights
+    y64 = y.astype(np.float64)
+    mu, var = y64.mean(1, keepdims=True), y64.var(1, keepdims=True)
+    z = (y16.astype(np.float64) - mu) / np.sqrt(var + eps)
+    ref = z @ (W * gamma[None, :]).astype(np.float16).astype(np.float64).T + cvec
+    if epi == 1:
+        from scipy.special import erf
+
+        ref = ref * 0.5 * (1.0 + erf(ref / np.sqrt(2.0)))
+    err = np.abs(out.astype(np.float64) - ref)
+    tol = 2e-3 * np.abs(ref) + 3e-3
+    assert (err <= tol).all(), (float(err.max()), np.argwhere(err > tol)[:4])
+    # and it is a faithful LayerNorm + projection: against the unrounded computation
+    full = ((y64 - mu) / np.sqrt(var + eps) * gamma + beta) @ W.astype(np.float64).T + b
+    if epi == 0:
+        assert np.abs(out.astype(np.float64) - full).max() < 0.05 * np.abs(full).max()
+
+
+@pytest.mark.parametrize("M,K", [(384, 768), (1000, 3072), (148 * 256 + 3, 768)])
+def test_gemm_residual_layernorm_epilogue_and_row_statistics(rt, M, K):
+    """attention-out / FFN2: y' = acc + bias + LN(y) with the LayerNorm re-applied from the row's partial statistics, the
+    new rows' statistics emitted as (sum, M2) partials per 128 columns."""
+    N, eps = 768, 1e-12
+    rng = np.random.default_rng(M + K)
+    a = rng.standard_normal((M, K)).astype(np.float16)
+    w = (rng.standard_normal((N, K)) * 0.05).astype(np.float16)
+    bias = rng.standard_normal(N).astype(np.float32)
+    resid = (rng.standard_normal((M, N)) * 2.0 - 0.5).astype(np.float32)
+    resid[:, 381] -= 55.0
+    # the kernel sees the residual as fp16 hi + fp16 lo
+    hi = resid.astype(np.float16)
+    res22 = hi.astype(np.float32) + (resid - hi.astype(np.float32)).astype(np.float16).astype(np.float32)
+    gamma = (1.5 + 0.4 * rng.standard_normal(N)).astype(np.float32)
+    beta = (0.3 * rng.standard_normal(N)).astype(np.float32)
+    out, _, st = rt.debug_gemm(2, a, w, bias, resid, ln_stats=_partials(res22), ln_gamma=gamma, ln_beta=beta, eps=eps, want_stats=True)
+    r64 = res22.astype(np.float64)
+    ln = (r64 - r64.mean(1, keepdims=True)) / np.sqrt(r64.var(1, keepdims=True) + eps) * gamma + beta
+    ref = a.astype(np.float64) @ w.astype(np.float64).T + bias + ln
+    err = np.abs(out - ref)
+    tol = 1e-4 * np.abs(ref) + 2e-4
+    assert (err <= tol).all(), (float(err.max()), np.argwhere(err > tol)[:4])
+    want = _partials(ref.astype(np.float32))
+    assert np.allclose(st[..., 0], want[..., 0], rtol=1e-4, atol=2e-2), float(np.abs(st[..., 0] - want[..., 0]).max())
+    assert np.allclose(st[..., 1], want[..., 1], rtol=2e-4, atol=1e-2), float(np.abs(st[..., 1] - want[..., 1]).max())
 
 
 @pytest.mark.parametrize("B,S,lens", [(1, 128, [128]), (2, 512, [512, 512]), (3, 300, [300, 17, 129]), (4, 512, [512, 1, 128, 385]),

@@ -5,7 +5,7 @@ written as CUDA.
 
   mode "current": x16 = fp16(LN(y)) feeds QKV / FFN1 (round-1 design, LayerNorm kernels materialise x16)
   mode "fold"   : y16 = fp16(y) (the raw pre-LayerNorm residual) feeds QKV / FFN1 with gamma folded into the weight columns;
-                  the epilogue applies rstd * (acc - mean * colsum(W')) + (W beta + b)   (round-2 design, no LN kernels)
+                  and the weight rows centred; the epilogue applies rstd * acc + (W beta + b)   (round-2 design, no LN kernels)
 
     python tools/emulate_numerics.py [--style hf|trained|hard] [--layers 12] [--items 4] [--seq 512]
 """
@@ -55,11 +55,11 @@ def emulate(flat, ids, lens, g, mode="current", p_sum="exact", keep=()):
         if mode == "current":
             return r("x", ln_apply(y, ln)) @ r("w", W[w]).T + W[b]
         mu, rstd = stats(y, g.eps)
-        wp = r("w", W[w] * W[ln[0]][None, :])            # gamma folded into the columns, rounded once to fp16
-        acc = r("x", y) @ wp.T
-        wsum = wp.sum(1, dtype=np.float32)
+        wg = W[w] * W[ln[0]][None, :]
+        wp = r("w", wg - wg.mean(1, keepdims=True, dtype=np.float32))  # gamma folded into the columns, rows centred, rounded once
+        acc = r("x", y) @ wp.T                                         # the row mean cancels inside the GEMM
         c = W[w] @ W[ln[1]] + W[b]
-        return rstd * (acc - mu * wsum) + c
+        return rstd * acc + c
 
     for l in range(g.layers):
         p = f"l{l}."

@@ -19,7 +19,8 @@ for M, N, K, epi in [(32768, 2304, 768, 0), (32768, 768, 3072, 2), (32768, 3072,
         ms = ctypes.c_float(0)
         lib = b200rt.load_library()
         rc = lib.b200rt_debug_gemm(epi | ((mode | (nst << 4)) << 8), a.ctypes.data_as(ctypes.c_void_p), w.ctypes.data_as(ctypes.c_void_p), bias.ctypes.data_as(ctypes.c_void_p),
-                                   resid.ctypes.data_as(ctypes.c_void_p) if resid is not None else None, out.ctypes.data_as(ctypes.c_void_p), M, N, K, 20, ctypes.byref(ms))
+                                   resid.ctypes.data_as(ctypes.c_void_p) if resid is not None else None, out.ctypes.data_as(ctypes.c_void_p), M, N, K, 20, ctypes.byref(ms),
+                                   None, None, None, 1e-12, None)
         assert rc == 0, lib.b200rt_last_error()
         c = dict(M=M, N=N, K=K, epi=epi, mode=["normal", "mma_only", "tma_only"][mode], stages=nst or 6, ms=ms.value, tflops_equiv=2.0 * M * N * K / ms.value / 1e9)
         res.append(c); print(c, flush=True)

@@ -19,7 +19,7 @@ def to_bytes(r, name):
 def role(r):
     n = r[idx["Kernel Name"]]
     for key, name in (("gemm_pair_kernel<0>", "gemm_qkv"), ("gemm_pair_kernel<1>", "gemm_ffn1_gelu"), ("gemm_pair_kernel<2>", "gemm_res"),
-                      ("attention_kernel", "attention"), ("embed_ln", "embed_ln"), ("ln_kernel", "ln1"), ("pool_normalize", "pool_normalize"),
+                      ("attention_kernel", "attention"), ("embed_kernel", "embed"), ("pool_normalize", "pool_normalize"),
                       ("scatter", "scatter")):
         if key in n:
             return name
@@ -36,8 +36,6 @@ for r in rows[2:]:
 if "gemm_res" in seen:  # the residual epilogue serves attn-out (K = 768) and FFN2 (K = 3072): tell them apart by duration
     rs = sorted(seen.pop("gemm_res"), key=lambda r: float(r[idx["gpu__time_duration.sum"]]))
     seen["gemm_attn_out"], seen["gemm_ffn2"] = [rs[0]], [rs[-1]]
-if "ln1" in seen:
-    seen["ln2"] = seen["ln1"]
 for name, rs in seen.items():
     r = rs[-1]
     b = to_bytes(r, "dram__bytes_read.sum") + to_bytes(r, "dram__bytes_write.sum")
