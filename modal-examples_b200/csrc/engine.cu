@@ -310,7 +310,7 @@ int forward_enqueue(Dev& d, const Model& m, int dev_index, const int32_t* ids, c
         GemmEpi e_qkv{lw.qkv_c, d.pstats[0], STAT_PARTS, nullptr, nullptr, nullptr, c.eps};
         CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_yhi, lw.m_qkv, d.m_qkv2d, nullptr, e_qkv, M, QKV_DIM, HIDDEN, d.sm_count, stream));
         ++nl; mark("gemm_qkv");
-        CUDA_TRY(launch_attention(*mq, *mc, lens, B, S, stream));
+        CUDA_TRY(launch_attention(*mq, *mc, lens, B, S, d.sm_count, stream));
         ++nl; mark("attention");
         // y <- ctx Wao^T + b + LN_prev(y); new row statistics (LN1's) into pstats[1]
         GemmEpi e_ao{lw.ao_b, d.pstats[0], STAT_PARTS, prev_g, prev_b, d.pstats[1], c.eps};
@@ -1437,21 +1437,22 @@ int b200rt_debug_attention(const uint16_t* qkv, const int32_t* lens, uint16_t* c
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     if (iters < 1) iters = 1;
-    CUDA_TRY(launch_attention(tq, tc, dl_, B, S, d.compute));
+    CUDA_TRY(launch_attention(tq, tc, dl_, B, S, d.sm_count, d.compute));
     CUDA_TRY(cudaEventRecord(e0, d.compute));
-    for (int i = 0; i < iters; ++i) CUDA_TRY(launch_attention(tq, tc, dl_, B, S, d.compute));
+    for (int i = 0; i < iters; ++i) CUDA_TRY(launch_attention(tq, tc, dl_, B, S, d.sm_count, d.compute));
     CUDA_TRY(cudaEventRecord(e1, d.compute));
     CUDA_TRY(cudaStreamSynchronize(d.compute));
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     if (ms_out) *ms_out = ms / iters;
     CUDA_TRY(cudaMemcpy(ctx, dc, M * HIDDEN * 2, cudaMemcpyDeviceToHost));
+#ifdef B200RT_DIAG
     if (const char* path = getenv("B200RT_ATTN_STAMPS")) {  // diagnostics: per-phase clock stamps of CTA 0 -> text file
         unsigned long long* dstamp = nullptr;
         std::vector<unsigned long long> hs(5 * 32 * 8, 0);
         CUDA_TRY(cudaMalloc(&dstamp, hs.size() * 8));
         CUDA_TRY(cudaMemset(dstamp, 0, hs.size() * 8));
-        CUDA_TRY(launch_attention(tq, tc, dl_, B, S, d.compute, dstamp));
+        CUDA_TRY(launch_attention(tq, tc, dl_, B, S, d.sm_count, d.compute, dstamp));
         CUDA_TRY(cudaStreamSynchronize(d.compute));
         CUDA_TRY(cudaMemcpy(hs.data(), dstamp, hs.size() * 8, cudaMemcpyDeviceToHost));
         unsigned long long t0 = ~0ull;
@@ -1474,6 +1475,7 @@ int b200rt_debug_attention(const uint16_t* qkv, const int32_t* lens, uint16_t* c
         }
         cudaFree(dstamp);
     }
+#endif
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(dq); cudaFree(dc); cudaFree(dl_);
     return 0;

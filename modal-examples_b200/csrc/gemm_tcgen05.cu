@@ -241,34 +241,59 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         uint32_t aphase = 0;
         uint32_t g = 0;  // staging-buffer use counter of this half
         int tpar = 0;
+        // Per-tile inputs of this thread -- its row's statistic partials and its column's epilogue vector entries -- are
+        // fetched one tile AHEAD: their global-load latency (two dependent round trips when done at the top of the tile) sat
+        // on the epilogue's critical path and cost FFN1, whose GELU epilogue has no slack against the MMAs, ~15 %.
+        const bool has_ln = ep.stats_in != nullptr;
+        float4 pf_st[3] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+        float pf_bias = 0.f, pf_g = 1.f, pf_b = 0.f;
+        auto prefetch = [&](int tile_) {
+            if (tile_ >= num_tiles) return;
+            const int n_blk_ = tile_ % num_n;
+            const int col_ = n_blk_ * BN + h * (BN / 2) + r;
+            pf_bias = __ldg(bias + col_);
+            if constexpr (EPI == EPI_BIAS_RES_SPLIT) {
+                if (has_ln) {
+                    pf_g = __ldg(ep.ln_gamma + col_);
+                    pf_b = __ldg(ep.ln_beta + col_);
+                }
+            }
+            if (has_ln) {
+                const int grow_ = (tile_ / num_n) * (2 * BM) + cta_rank * BM + r;
+                const float4* __restrict__ pp = reinterpret_cast<const float4*>(ep.stats_in + static_cast<size_t>(grow_) * STAT_PARTS);
+                pf_st[0] = __ldg(pp);
+                pf_st[1] = __ldg(pp + 1);
+                pf_st[2] = __ldg(pp + 2);
+            }
+        };
+        prefetch(pair);
         for (int tile = pair; tile < num_tiles; tile += num_pairs, tpar ^= 1) {
             const int n_blk = tile % num_n;
             const int grow = (tile / num_n) * (2 * BM) + cta_rank * BM + r;  // this thread's global row
             // stage this tile's per-column vectors (128 floats per half) once; double buffered across tiles
-            const uint32_t sb = smem_u32(sbias + tpar * 768 + h * 128);  // bias; wsum|gamma at +256 floats, beta at +512
-            const int col = n_blk * BN + h * (BN / 2) + r;
-            sts32f(sb + r * 4, __ldg(bias + col));
-            // statistics of the LayerNorm this epilogue folds (EPI 0/1) or re-applies to the residual (EPI 2)
+            const uint32_t sb = smem_u32(sbias + tpar * 768 + h * 128);  // bias; gamma at +256 floats, beta at +512
+            sts32f(sb + r * 4, pf_bias);
+            if constexpr (EPI == EPI_BIAS_RES_SPLIT) {
+                sts32f(sb + 1024 + r * 4, pf_g);
+                sts32f(sb + 2048 + r * 4, pf_b);
+            }
+            // statistics of the LayerNorm this epilogue folds (EPI 0/1) or re-applies to the residual (EPI 2): combine the
+            // row's (sum, M2) partials
             float ln_mean = 0.f, ln_rstd = 1.f;
-            const bool has_ln = ep.stats_in != nullptr;
             if (has_ln) {
-                const float2* __restrict__ pp = ep.stats_in + static_cast<size_t>(grow) * ep.parts_in;
-                float sum = 0.f;
-                for (int j = 0; j < ep.parts_in; ++j) sum += __ldg(&pp[j].x);
-                const float inv_n = 1.0f / (128.0f * ep.parts_in);
-                ln_mean = sum * inv_n;
-                float m2 = 0.f;
-                for (int j = 0; j < ep.parts_in; ++j) {
-                    const float2 pj = __ldg(&pp[j]);
+                const float2 p0 = make_float2(pf_st[0].x, pf_st[0].y), p1 = make_float2(pf_st[0].z, pf_st[0].w);
+                const float2 p2 = make_float2(pf_st[1].x, pf_st[1].y), p3 = make_float2(pf_st[1].z, pf_st[1].w);
+                const float2 p4 = make_float2(pf_st[2].x, pf_st[2].y), p5 = make_float2(pf_st[2].z, pf_st[2].w);
+                constexpr float inv_n = 1.0f / (128.0f * STAT_PARTS);
+                ln_mean = (((p0.x + p1.x) + (p2.x + p3.x)) + (p4.x + p5.x)) * inv_n;
+                auto m2_of = [&](const float2& pj) {
                     const float d = pj.x * (1.0f / 128.0f) - ln_mean;
-                    m2 += fmaf(128.0f * d, d, pj.y);
-                }
+                    return fmaf(128.0f * d, d, pj.y);
+                };
+                const float m2 = ((m2_of(p0) + m2_of(p1)) + (m2_of(p2) + m2_of(p3))) + (m2_of(p4) + m2_of(p5));
                 ln_rstd = rsqrtf(m2 * inv_n + ep.eps);
             }
-            if constexpr (EPI == EPI_BIAS_RES_SPLIT) {
-                sts32f(sb + 1024 + r * 4, has_ln ? __ldg(ep.ln_gamma + col) : 1.0f);
-                sts32f(sb + 2048 + r * 4, has_ln ? __ldg(ep.ln_beta + col) : 0.0f);
-            }
+            prefetch(tile + num_pairs);  // in flight while this tile is processed
             named_bar_sync(1 + h, 128);
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
@@ -428,7 +453,7 @@ cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
     const int dbg_mode = epi >> 8;
     epi &= 0xFF;
     if (N % gemm::BN != 0 || K % gemm::BK != 0 || M <= 0 || e.bias == nullptr) return cudaErrorInvalidValue;
-    if (e.stats_in != nullptr && (e.parts_in < 1 || e.parts_in > 32)) return cudaErrorInvalidValue;
+    if (e.stats_in != nullptr && e.parts_in != STAT_PARTS) return cudaErrorInvalidValue;  // the LayerNorm'd width is HIDDEN
     switch (epi) {
         case EPI_BIAS_F16:
         case EPI_BIAS_GELU_F16:

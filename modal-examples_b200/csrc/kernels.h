@@ -57,9 +57,9 @@ cudaError_t launch_fold_ln(const float* w, const float* gamma, const float* beta
 
 // Multi-head self-attention over a padded batch: qkv fp16 [B, S, 2304] (Q | K | V, head-major within each),
 // lens[B] valid keys per item, ctx fp16 [B*S, 768].  tq: 3D map over qkv {2304, S, B}, tctx: 3D map over ctx {768, S, B};
-// both box {64,128,1}, 128B swizzle.
-// dbg: optional device buffer of 5*32*8 clock stamps written by CTA 0 (diagnostics; NULL in the product path)
-cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tctx, const int32_t* lens, int B, int S,
+// both box {64,128,1}, 128B swizzle.  Persistent: min(units, sm_count) CTAs walk the (item, head[, query tile]) units.
+// dbg: B200RT_DIAG builds only -- device buffer of 5*32*8 clock stamps written by CTA 0 (NULL in the product path)
+cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tctx, const int32_t* lens, int B, int S, int sm_count,
                              cudaStream_t stream, unsigned long long* dbg = nullptr);
 
 // word + position + token_type(0) embedding gather -> y = hi + lo (pre-LN residual stream) + the row's statistic partials.

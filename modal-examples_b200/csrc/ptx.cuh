@@ -77,6 +77,10 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     return t;
 }
 
+#ifdef B200RT_DIAG
+__device__ uint32_t g_attn_prog = 0;  // shared-memory address of the attention kernel's per-role progress words (diagnostics)
+#endif
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const uint64_t t0 = global_timer_ns();
@@ -85,6 +89,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if ((++spins & 0x3FF) == 0 && global_timer_ns() - t0 > 4000000000ull) {
             printf("b200rt: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x,
                    (int)threadIdx.x, smem_u32(bar), parity);
+#ifdef B200RT_DIAG
+            if (g_attn_prog != 0) {
+                for (int role = 0; role < 8; ++role) {
+                    uint32_t a, b, c;
+                    asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(a) : "r"(g_attn_prog + role * 16));
+                    asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(b) : "r"(g_attn_prog + role * 16 + 4));
+                    asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(c) : "r"(g_attn_prog + role * 16 + 8));
+                    printf("   block %d role %d: unit %u sub-block %u step %u\n", (int)blockIdx.x, role, a, b, c);
+                }
+            }
+#endif
             __trap();
         }
     }
