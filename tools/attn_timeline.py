@@ -7,6 +7,7 @@ out = os.path.join(ROOT, "gpurun_out", "attn_timeline.txt")
 os.makedirs(os.path.dirname(out), exist_ok=True)
 os.environ["B200RT_ATTN_STAMPS"] = out
 import numpy as np, b200rt
+b200rt.LIB_PATH = os.path.join(ROOT, "modal-examples_b200", "libb200rt_diag.so")  # `make -C modal-examples_b200/csrc diag`
 b200rt.init(1)
 rng = np.random.default_rng(0)
 B, S = 64, 512
