@@ -417,6 +417,32 @@ def main_ours(args):
     dev_out = np.concatenate([dev[r]["out"].cpu().numpy() for r in range(N)])
     assert float(np.abs(dev_out - e2e_out).max()) < 1e-5, "device-resident and host-buffer paths disagree"
 
+    # ---------------- ragged lengths (uniform 16..512, seed 1: SURVEY.md section 8(d)'s correctness variant) at throughput: the
+    # same submit/wait path; items travel in 64-token length buckets, so tokens/s should stay near the full-length figure
+    rng_r = np.random.default_rng(1)
+    r_lens = rng_r.integers(16, SEQ + 1, size=n_total).astype(np.int32)
+    pin_lens = b200rt.PinnedBuffer((n_total,), np.int32)
+    pin_lens.array[:] = r_lens
+
+    def ragged_step():
+        tk = [model.submit(pin_ids.array[j * MAP_INPUT_ITEMS:(j + 1) * MAP_INPUT_ITEMS], pin_lens.array[j * MAP_INPUT_ITEMS:(j + 1) * MAP_INPUT_ITEMS],
+                           out=pin_out.array[j * MAP_INPUT_ITEMS:(j + 1) * MAP_INPUT_ITEMS], borrow_ids=True) for j in range(n_inputs)]
+        for t in tk:
+            model.wait(t)
+
+    ragged_step()
+    sync_all()
+    t0 = time.perf_counter()
+    r_steps = max(2, args.steps // 4)
+    for _ in range(r_steps):
+        ragged_step()
+    sync_all()
+    ragged_s = time.perf_counter() - t0
+    assert np.allclose(np.linalg.norm(pin_out.array, axis=1), 1.0, atol=1e-3)
+    ragged = {"lens": "uniform 16..512 (numpy default_rng(1))", "items_per_s": r_steps * n_total / ragged_s,
+              "tokens_per_s": r_steps * float(r_lens.sum()) / ragged_s}
+    pin_lens.free()
+
     # ---------------- the device-resident loop once more, now on chips as warm as the e2e loop saw them: separates the
     # cost of the host path from power-cap clock drift between the two timed regions
     dev_ms_after = device_loop(args.steps, True)
@@ -482,6 +508,8 @@ def main_ours(args):
     total_items = args.steps * n_total
     value = total_items / (dev_ms / 1e3)
     e2e_value = total_items / e2e_s
+    ragged["tokens_per_s_full_length"] = e2e_value * SEQ
+    ragged["tokens_per_s_ratio"] = ragged["tokens_per_s"] / (e2e_value * SEQ)
 
     # ---------------- roofline of the dominant kernel (device events between launches, compute stream, sustained loop)
     top = max((k for k in prof if k in KERNEL_FLOPS), key=lambda k: prof[k])
@@ -537,7 +565,7 @@ def main_ours(args):
                 "api": "b200rt_submit_ex(BORROW_IDS)/b200rt_wait (C ABI; ids and out in b200rt_alloc_pinned memory, DMA'd in place)",
                 "device_resident_rerun_after_e2e": total_items / (dev_ms_after / 1e3),
                 "per_step_ms": {k: (s1[k] - s0[k]) / args.steps / 1e3 for k in ("stage_us", "dispatch_us", "h2d_scatter_us", "forward_us", "gap_us", "d2h_us")}},
-        "e2e_map": e2e_map,
+        "e2e_map": e2e_map, "ragged": ragged,
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "latency": {"p50_ms": p50_ms, "p99_ms": p99_ms, "what": "one 512-token item, b200rt_submit_ex+b200rt_wait, pinned host buffers, 1000 trials after 100 warm-ups",
                     "shim_remote_p50_ms": lat_map[len(lat_map) // 2], "shim_remote_p99_ms": lat_map[int(len(lat_map) * 0.99) - 1]},

@@ -6,6 +6,7 @@
 // last kernel stores straight into the root's gather buffer, then one D2H) -> completer (waits the wave's
 // event, hands rows to the tickets' caller-owned buffers, wakes waiters).  No NCCL call and no host
 // round-trip between H2D and D2H.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -199,7 +200,10 @@ struct Ticket {
     std::vector<int32_t> lens;
     int n_items, S;
     float* out;
-    int next_item = 0;          // dispatcher cursor
+    // Items travel in length buckets of 64 tokens (each bucket is padded to its own length, not to the input's max_len):
+    // `order` lists the item indices sorted by bucket (stable), empty when that is the identity (all items in one bucket).
+    std::vector<int32_t> order;
+    int item_at(int pos) const { return order.empty() ? pos : order[pos]; }
     std::atomic<int> remaining; // items not yet delivered
     bool done = false;
     int waiters = 0;            // threads blocked in b200rt_wait on this ticket: poll_any must not hand it out
@@ -207,9 +211,16 @@ struct Ticket {
     std::string error;
 };
 
+// A run of a ticket's items that share a length bucket: positions [begin, begin + count) of the ticket's `order`.
+struct Run {
+    std::shared_ptr<Ticket> t;
+    int begin, count, bucket;
+    int next = 0;  // dispatcher cursor within the run
+};
+
 struct Segment {
     std::shared_ptr<Ticket> t;
-    int ticket_off, count, wave_off;
+    int ticket_off, count, wave_off;  // ticket_off: position in the ticket's `order`
 };
 
 struct Wave {
@@ -235,12 +246,13 @@ struct Runtime {
     // queues
     std::mutex mu;
     std::condition_variable cv_submit, cv_done, cv_slot, cv_wave, cv_idle;
-    std::deque<std::shared_ptr<Ticket>> pending;
+    std::deque<Run> pending;  // runs in arrival order; a wave takes the front run's bucket and every later run of that bucket
     std::unordered_map<uint64_t, std::shared_ptr<Ticket>> tickets;
     std::deque<uint64_t> finished_unclaimed;
     std::deque<Wave> inflight;
     bool slot_busy[NSLOT] = {};
     int fill_window_us = 200;
+    std::chrono::steady_clock::time_point last_submit = std::chrono::steady_clock::now();
     int active_calls = 0;  // threads inside b200rt_wait / b200rt_poll_any (shutdown waits for them to leave)
     uint64_t next_ticket = 1, next_wave = 0;
     bool stopping = false;
@@ -504,41 +516,51 @@ void dispatcher_main(Runtime* rtp) {
             rt.cv_slot.wait(lk, [&] { return rt.stopping || !rt.slot_busy[slot]; });
             if (rt.stopping) return;
             if (rt.pending.empty()) continue;
-            // Fill window: while earlier waves keep the GPUs busy, give a partial wave up to FILL_WINDOW_US to grow
-            // (an idle pool dispatches at once: that is the latency path).
+            // Fill policy: a wave that would go out partial waits while submissions keep arriving -- until it is full, or no
+            // ticket has arrived for a quiet period (pool busy: 200 us; idle: 40 us, the latency path), or a hard limit
+            // (busy 2 ms, idle 1 ms).  A burst of small inputs hitting an idle pool (the start of every .map()) would otherwise
+            // go out as a train of fragments, one per free wave slot.
             {
-                const int S0 = bucket_of(rt.pending.front()->S);
+                const int S0 = rt.pending.front().bucket;
+                const Model* m0 = rt.pending.front().t->mp;
                 const int cap0 = (rt.cap_rows / S0) * G;
                 auto queued = [&] {
                     int n = 0;
-                    for (auto& t : rt.pending) n += t->n_items - t->next_item;
+                    for (auto& r : rt.pending)
+                        if (r.bucket == S0 && r.t->mp == m0) n += r.count - r.next;
                     return n;
                 };
                 bool busy = false;
                 for (int s2 = 0; s2 < NSLOT; ++s2) busy |= rt.slot_busy[s2];
-                if (busy && queued() < cap0) {
-                    const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(rt.fill_window_us);
-                    rt.cv_submit.wait_until(lk, deadline, [&] { return rt.stopping || queued() >= cap0; });
+                const auto quiet = std::chrono::microseconds(busy ? rt.fill_window_us : rt.fill_window_us / 5);
+                const auto hard = std::chrono::steady_clock::now() + std::chrono::microseconds(busy ? 10 * rt.fill_window_us : 5 * rt.fill_window_us);
+                while (!rt.pending.empty() && queued() < cap0) {
+                    const auto now = std::chrono::steady_clock::now();
+                    const auto deadline = std::min(hard, rt.last_submit + quiet);
+                    if (now >= deadline) break;
+                    rt.cv_submit.wait_until(lk, deadline);
                     if (rt.stopping) return;
-                    if (rt.pending.empty()) continue;
                 }
+                if (rt.pending.empty()) continue;
             }
             rt.slot_busy[slot] = true;
             rt.next_wave++;
             wv.slot = slot;
-            wv.S = bucket_of(rt.pending.front()->S);
+            wv.S = rt.pending.front().bucket;
             wv.n_items = 0;
-            const Model* model = rt.pending.front()->mp;
+            const Model* model = rt.pending.front().t->mp;
             // token capacity scales with 512/S: a wave holds cap_rows tokens per replica
             const int cap_items_S = (rt.cap_rows / wv.S) * G;
-            while (!rt.pending.empty() && wv.n_items < cap_items_S) {
-                auto t = rt.pending.front();
-                if (bucket_of(t->S) != wv.S || t->mp != model) break;
-                const int take = std::min(t->n_items - t->next_item, cap_items_S - wv.n_items);
-                wv.segs.push_back(Segment{t, t->next_item, take, wv.n_items});
-                t->next_item += take;
+            for (auto it = rt.pending.begin(); it != rt.pending.end() && wv.n_items < cap_items_S;) {
+                if (it->bucket != wv.S || it->t->mp != model) {
+                    ++it;
+                    continue;
+                }
+                const int take = std::min(it->count - it->next, cap_items_S - wv.n_items);
+                wv.segs.push_back(Segment{it->t, it->begin + it->next, take, wv.n_items});
+                it->next += take;
                 wv.n_items += take;
-                if (t->next_item == t->n_items) rt.pending.pop_front();
+                it = it->next == it->count ? rt.pending.erase(it) : it + 1;
             }
         }
         const int slot = wv.slot, S = wv.S, n = wv.n_items;
@@ -550,29 +572,34 @@ void dispatcher_main(Runtime* rtp) {
         // wave's own padded length, is DMA'd from where it lies; anything else goes through the slot's pinned buffer
         // (re-strided to the bucket length when the ticket's max_len is shorter).
         bool staged = false;
+        auto direct_ids = [&](const Segment& sg) {  // lent, pinned, already at the wave's padded length, items in place
+            const Ticket& t = *sg.t;
+            return t.borrowed && t.ids_pinned && t.S == S && t.order.empty();
+        };
         for (const Segment& sg : wv.segs) {
             const Ticket& t = *sg.t;
-            const int32_t* src = t.ids_ptr() + static_cast<size_t>(sg.ticket_off) * t.S;
             int32_t* hdst = rt.h_ids[slot] + static_cast<size_t>(sg.wave_off) * S;
-            if (t.borrowed && t.S == S && t.ids_pinned) {
-                SCHED_TRY(cudaMemcpyAsync(rt.d_ids_stage[slot] + static_cast<size_t>(sg.wave_off) * S, src,
+            if (direct_ids(sg)) {
+                SCHED_TRY(cudaMemcpyAsync(rt.d_ids_stage[slot] + static_cast<size_t>(sg.wave_off) * S,
+                                          t.ids_ptr() + static_cast<size_t>(sg.ticket_off) * t.S,
                                           static_cast<size_t>(sg.count) * S * 4, cudaMemcpyHostToDevice, rt.s_in));
                 wv.direct_h2d = true;
-                // keep the pinned mirror coherent for the bulk copy below (cheap: it is skipped when every segment is direct)
                 continue;
             }
             staged = true;
-            if (t.S == S) {
-                memcpy(hdst, src, static_cast<size_t>(sg.count) * S * 4);
-            } else {
+            if (t.S == S && t.order.empty()) {
+                memcpy(hdst, t.ids_ptr() + static_cast<size_t>(sg.ticket_off) * t.S, static_cast<size_t>(sg.count) * S * 4);
+            } else {  // re-stride to the bucket length (every item of the run has len <= S), gathering through `order`
+                const int ncopy = std::min(t.S, S);
                 for (int i = 0; i < sg.count; ++i) {
-                    memcpy(hdst + static_cast<size_t>(i) * S, src + static_cast<size_t>(i) * t.S, static_cast<size_t>(t.S) * 4);
-                    memset(hdst + static_cast<size_t>(i) * S + t.S, 0, static_cast<size_t>(S - t.S) * 4);
+                    const int32_t* src = t.ids_ptr() + static_cast<size_t>(t.item_at(sg.ticket_off + i)) * t.S;
+                    memcpy(hdst + static_cast<size_t>(i) * S, src, static_cast<size_t>(ncopy) * 4);
+                    if (S > ncopy) memset(hdst + static_cast<size_t>(i) * S + ncopy, 0, static_cast<size_t>(S - ncopy) * 4);
                 }
             }
         }
         for (const Segment& sg : wv.segs)
-            memcpy(rt.h_lens[slot] + sg.wave_off, sg.t->lens.data() + sg.ticket_off, static_cast<size_t>(sg.count) * 4);
+            for (int i = 0; i < sg.count; ++i) rt.h_lens[slot][sg.wave_off + i] = sg.t->lens[sg.t->item_at(sg.ticket_off + i)];
         auto t_host1 = std::chrono::steady_clock::now();
         if (staged) {
             if (!wv.direct_h2d) {
@@ -580,8 +607,7 @@ void dispatcher_main(Runtime* rtp) {
                                           cudaMemcpyHostToDevice, rt.s_in));
             } else {  // mixed wave: only the staged segments come from the slot buffer
                 for (const Segment& sg : wv.segs) {
-                    const Ticket& t = *sg.t;
-                    if (t.borrowed && t.S == S && t.ids_pinned) continue;
+                    if (direct_ids(sg)) continue;
                     SCHED_TRY(cudaMemcpyAsync(rt.d_ids_stage[slot] + static_cast<size_t>(sg.wave_off) * S,
                                               rt.h_ids[slot] + static_cast<size_t>(sg.wave_off) * S,
                                               static_cast<size_t>(sg.count) * S * 4, cudaMemcpyHostToDevice, rt.s_in));
@@ -682,7 +708,7 @@ void dispatcher_main(Runtime* rtp) {
         // D2H: rows of a ticket whose `out` lies in pinned memory go straight there; the rest through the slot buffer
         bool any_staged_out = false;
         for (const Segment& sg : wv.segs) {
-            if (!sg.t->out_pinned) { any_staged_out = true; continue; }
+            if (!(sg.t->out_pinned && sg.t->order.empty())) { any_staged_out = true; continue; }
             SCHED_TRY(cudaMemcpyAsync(sg.t->out + static_cast<size_t>(sg.ticket_off) * HIDDEN,
                                       rt.d_out_gather[slot] + static_cast<size_t>(sg.wave_off) * HIDDEN,
                                       static_cast<size_t>(sg.count) * HIDDEN * 4, cudaMemcpyDeviceToHost, rt.s_out));
@@ -749,11 +775,17 @@ void completer_main(Runtime* rtp) {
             {
                 std::lock_guard<std::mutex> lk(rt.mu);
                 for (const Segment& sg : wv.segs)
-                    if (!sg.t->done && !sg.t->out_pinned) live.push_back(&sg);
+                    if (!sg.t->done && !(sg.t->out_pinned && sg.t->order.empty())) live.push_back(&sg);
             }
-            for (const Segment* sg : live)
-                memcpy(sg->t->out + static_cast<size_t>(sg->ticket_off) * HIDDEN,
-                       rt.h_out[slot] + static_cast<size_t>(sg->wave_off) * HIDDEN, static_cast<size_t>(sg->count) * HIDDEN * 4);
+            for (const Segment* sg : live) {
+                const float* src = rt.h_out[slot] + static_cast<size_t>(sg->wave_off) * HIDDEN;
+                if (sg->t->order.empty()) {
+                    memcpy(sg->t->out + static_cast<size_t>(sg->ticket_off) * HIDDEN, src, static_cast<size_t>(sg->count) * HIDDEN * 4);
+                } else {  // rows go back to the items' own positions
+                    for (int i = 0; i < sg->count; ++i)
+                        memcpy(sg->t->out + static_cast<size_t>(sg->t->order[sg->ticket_off + i]) * HIDDEN, src + static_cast<size_t>(i) * HIDDEN, HIDDEN * 4);
+                }
+            }
         }
         {
             std::lock_guard<std::mutex> sl(rt.stats_mu);
@@ -1094,12 +1126,35 @@ static int submit_impl(int model, const int32_t* ids, const int32_t* lens, int n
     t->out_pinned = is_pinned(out, static_cast<size_t>(n_items) * HIDDEN * 4);
     if (lens) t->lens.assign(lens, lens + n_items);
     else t->lens.assign(n_items, max_len);
+    // runs of items per 64-token length bucket (TEI batches by token budget, un-padded; here every bucket is padded to its
+    // own length, so a ragged input wastes at most 63 tokens per item instead of max_len - len)
+    std::vector<Run> runs;
+    {
+        bool one_bucket = true;
+        const int b0 = bucket_of(t->lens[0]);
+        for (int i = 1; i < n_items && one_bucket; ++i) one_bucket = bucket_of(t->lens[i]) == b0;
+        if (one_bucket) {
+            runs.push_back(Run{t, 0, n_items, b0});
+        } else {
+            t->order.resize(n_items);
+            for (int i = 0; i < n_items; ++i) t->order[i] = i;
+            std::stable_sort(t->order.begin(), t->order.end(), [&](int a, int b) { return bucket_of(t->lens[a]) < bucket_of(t->lens[b]); });
+            for (int i = 0; i < n_items;) {
+                const int bk = bucket_of(t->lens[t->order[i]]);
+                int j = i;
+                while (j < n_items && bucket_of(t->lens[t->order[j]]) == bk) ++j;
+                runs.push_back(Run{t, i, j - i, bk});
+                i = j;
+            }
+        }
+    }
     {
         std::lock_guard<std::mutex> lk(rt->mu);
         if (rt->stopping) return fail(B200RT_E_STATE, "runtime is shutting down");
         t->id = rt->next_ticket++;
         rt->tickets.emplace(t->id, t);
-        rt->pending.push_back(t);
+        for (auto& r : runs) rt->pending.push_back(r);
+        rt->last_submit = std::chrono::steady_clock::now();
         *ticket_out = t->id;
     }
     rt->cv_submit.notify_one();

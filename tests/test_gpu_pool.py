@@ -152,6 +152,37 @@ def test_tickets_of_different_max_len_share_a_wave(pool):
         assert rt.poll_any(120_000) is not None
 
 
+def test_ragged_input_is_split_into_length_buckets(pool):
+    """One input with lengths 1..512: its items travel in 64-token length buckets (each padded to its own bucket, not to the
+    input's max_len), come back in the input's order, and every item equals the embedding it gets alone."""
+    rt, model, g, flat, G = pool
+    n = 96
+    ids, lens = R.synth_ragged(n, 512, seed=41, min_len=1)
+    s0 = rt.stats()
+    got = model.embed(ids, lens)
+    s1 = rt.stats()
+    tokens_padded_to_max = n * 512
+    moved = s1["h2d_bytes"] - s0["h2d_bytes"] - 4 * n
+    assert moved < 0.75 * 4 * tokens_padded_to_max, "ids were staged at max_len instead of per-bucket lengths"
+    assert moved >= 4 * int(lens.sum())
+    for i in (0, 1, 17, 50, 95):
+        L = int(lens[i])
+        alone = model.embed(ids[i:i + 1, :L].copy(), lens[i:i + 1])
+        assert np.array_equal(got[i:i + 1], alone), i
+    ref = R.forward_np(flat, ids[:4], lens[:4], g, dtype=np.float64)
+    assert R.rel_l2(got[:4], ref).max() <= 1e-3
+    # pinned, lent buffers take the same route
+    pin_ids = rt.PinnedBuffer((n, 512), np.int32)
+    pin_out = rt.PinnedBuffer((n, 768), np.float32)
+    try:
+        pin_ids.array[:] = ids
+        assert model.wait(model.submit(pin_ids.array, lens, out=pin_out.array, borrow_ids=True), 60_000) is not None
+        assert np.array_equal(pin_out.array, got)
+    finally:
+        pin_ids.free()
+        pin_out.free()
+
+
 def test_callers_stream_and_scheduler_are_ordered_on_the_workspace(pool):
     """b200rt_embed_device on a caller's stream and submit/wait traffic share one workspace per replica; the
     library orders them on the device, so interleaving them must not corrupt either."""
