@@ -209,3 +209,102 @@ def resolve_hub_snapshot(cache_dir: str, model_id: str) -> str | None:
         return None
     revs = sorted(os.listdir(root))
     return os.path.join(root, revs[-1]) if revs else None
+
+
+# ----------------------------------------------------------------------------------------------- CLIP ViT image tower
+# Second encoder on the same scheduler: openai/clip-vit-base-patch16's vision tower as served by the
+# reference's image-embedding example (06_gpu_and_ml/embeddings/image_embeddings_infinity.py:76-77, 298-306).
+# Blob order (fp32): patch.w [H, 3*p*p] (conv weight flattened channel, row, column) | cls [H] | pos [T, H] | pre.g | pre.b |
+# per layer: ln1.g ln1.b qkv.w [3H,H] qkv.b ao.w ao.b ln2.g ln2.b ff1.w [I,H] ff1.b ff2.w [H,I] ff2.b | post.g post.b | proj.w [P, H].
+
+CLIP_VIT_B16_GEOMETRY = dict(image=224, patch=16, hidden=768, layers=12, heads=12, inter=3072, proj=512, eps=1e-5)
+
+
+def vit_blob_layout(g: dict) -> list[tuple[str, tuple[int, ...]]]:
+    h, i = g["hidden"], g["inter"]
+    tokens = (g["image"] // g["patch"]) ** 2 + 1
+    lay = [("patch.w", (h, 3 * g["patch"] * g["patch"])), ("cls", (h,)), ("pos", (tokens, h)), ("pre.g", (h,)), ("pre.b", (h,))]
+    for l in range(g["layers"]):
+        p = f"l{l}."
+        lay += [(p + "ln1.g", (h,)), (p + "ln1.b", (h,)), (p + "qkv.w", (3 * h, h)), (p + "qkv.b", (3 * h,)),
+                (p + "ao.w", (h, h)), (p + "ao.b", (h,)), (p + "ln2.g", (h,)), (p + "ln2.b", (h,)),
+                (p + "ff1.w", (i, h)), (p + "ff1.b", (i,)), (p + "ff2.w", (h, i)), (p + "ff2.b", (h,))]
+    lay += [("post.g", (h,)), ("post.b", (h,)), ("proj.w", (g["proj"], h))]
+    return lay
+
+
+def vit_blob_numel(g: dict) -> int:
+    return sum(int(np.prod(s)) for _, s in vit_blob_layout(g))
+
+
+def random_vit_blob(g: dict = CLIP_VIT_B16_GEOMETRY, seed: int = 0) -> np.ndarray:
+    """Seeded weights of the geometry: normal sigma 0.02 matrices / embeddings, zero biases, unit LayerNorm."""
+    rng = np.random.default_rng(seed)
+    out = np.empty(vit_blob_numel(g), np.float32)
+    o = 0
+    for name, shape in vit_blob_layout(g):
+        n = int(np.prod(shape))
+        if name.endswith(".g"):
+            out[o:o + n] = 1.0
+        elif name.endswith(".b"):
+            out[o:o + n] = 0.0
+        else:
+            out[o:o + n] = (rng.standard_normal(shape, dtype=np.float32) * np.float32(0.02)).reshape(-1)
+        o += n
+    return out
+
+
+def load_clip_vision_state_dict(sd: dict, eps: float = 1e-5, heads: int | None = None) -> tuple[dict, np.ndarray]:
+    """HF ``CLIPModel`` / ``CLIPVisionModelWithProjection`` state dict -> (geometry, fp32 blob).  Parameter names as in HF
+    ``modeling_clip.py`` (``vision_model.embeddings.*``, ``vision_model.encoder.layers.N.*``, ``visual_projection.weight``)."""
+
+    def arr(v):
+        if hasattr(v, "detach"):
+            v = v.detach().to("cpu").float().numpy()
+        return np.ascontiguousarray(v, dtype=np.float32)
+
+    pw = arr(sd["vision_model.embeddings.patch_embedding.weight"])
+    h, _, p, _ = pw.shape
+    tokens = sd["vision_model.embeddings.position_embedding.weight"].shape[0]
+    layers = 0
+    while f"vision_model.encoder.layers.{layers}.self_attn.q_proj.weight" in sd:
+        layers += 1
+    grid = int(round((tokens - 1) ** 0.5))
+    g = dict(image=grid * p, patch=int(p), hidden=int(h), layers=layers, heads=int(heads or h // 64),
+             inter=int(sd["vision_model.encoder.layers.0.mlp.fc1.weight"].shape[0]), proj=int(sd["visual_projection.weight"].shape[0]), eps=float(eps))
+    out = np.empty(vit_blob_numel(g), np.float32)
+    o = 0
+
+    def put(a, shape):
+        nonlocal o
+        a = arr(a)
+        if a.shape != tuple(shape):
+            raise ValueError(f"checkpoint tensor has shape {a.shape}, geometry needs {tuple(shape)}")
+        out[o:o + a.size] = a.reshape(-1)
+        o += a.size
+
+    i = g["inter"]
+    put(pw.reshape(h, 3 * p * p), (h, 3 * p * p))
+    put(sd["vision_model.embeddings.class_embedding"], (h,))
+    put(sd["vision_model.embeddings.position_embedding.weight"], (tokens, h))
+    put(sd["vision_model.pre_layrnorm.weight"], (h,))
+    put(sd["vision_model.pre_layrnorm.bias"], (h,))
+    for l in range(layers):
+        s = f"vision_model.encoder.layers.{l}."
+        put(sd[s + "layer_norm1.weight"], (h,))
+        put(sd[s + "layer_norm1.bias"], (h,))
+        put(np.concatenate([arr(sd[s + f"self_attn.{n}.weight"]) for n in ("q_proj", "k_proj", "v_proj")], 0), (3 * h, h))
+        put(np.concatenate([arr(sd[s + f"self_attn.{n}.bias"]) for n in ("q_proj", "k_proj", "v_proj")], 0), (3 * h,))
+        put(sd[s + "self_attn.out_proj.weight"], (h, h))
+        put(sd[s + "self_attn.out_proj.bias"], (h,))
+        put(sd[s + "layer_norm2.weight"], (h,))
+        put(sd[s + "layer_norm2.bias"], (h,))
+        put(sd[s + "mlp.fc1.weight"], (i, h))
+        put(sd[s + "mlp.fc1.bias"], (i,))
+        put(sd[s + "mlp.fc2.weight"], (h, i))
+        put(sd[s + "mlp.fc2.bias"], (h,))
+    put(sd["vision_model.post_layernorm.weight"], (h,))
+    put(sd["vision_model.post_layernorm.bias"], (h,))
+    put(sd["visual_projection.weight"], (g["proj"], h))
+    assert o == out.size
+    return g, out

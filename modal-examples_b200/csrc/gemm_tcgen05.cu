@@ -64,6 +64,14 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return x * phi;
 }
 
+__device__ __forceinline__ float gelu_quick(float x) {
+    // CLIP's quick_gelu: x * sigmoid(1.702 x) = x / (1 + 2^(-1.702 log2(e) x)): 2 MUFU + 3 FMA-pipe ops
+    const float e = ex2_approx(x * (-1.702f * 1.4426950408889634f));
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
+
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -393,6 +401,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
                         for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
                     }
+                    if constexpr (EPI == EPI_BIAS_QGELU_F16) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = gelu_quick(v[j]);
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const uint32_t chunk = static_cast<uint32_t>((c & 1) * 4 + q) ^ swz;
@@ -444,6 +456,8 @@ cudaError_t gemm_init_device() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm::gemm_pair_kernel<EPI_BIAS_GELU_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm::gemm_pair_kernel<EPI_BIAS_QGELU_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(gemm::gemm_pair_kernel<EPI_BIAS_RES_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm::SMEM_BYTES);
 }
 
@@ -455,10 +469,9 @@ cudaError_t launch_gemm(int epi, const CUtensorMap& ta, const CUtensorMap& tb, c
     if (N % gemm::BN != 0 || K % gemm::BK != 0 || M <= 0 || e.bias == nullptr) return cudaErrorInvalidValue;
     if (e.stats_in != nullptr && e.parts_in != STAT_PARTS) return cudaErrorInvalidValue;  // the LayerNorm'd width is HIDDEN
     switch (epi) {
-        case EPI_BIAS_F16:
-        case EPI_BIAS_GELU_F16:
-            return epi == EPI_BIAS_F16 ? launch_pair<EPI_BIAS_F16>(ta, tb, tout, tout, e, M, N, K, sm_count, stream, dbg_mode)
-                                       : launch_pair<EPI_BIAS_GELU_F16>(ta, tb, tout, tout, e, M, N, K, sm_count, stream, dbg_mode);
+        case EPI_BIAS_F16: return launch_pair<EPI_BIAS_F16>(ta, tb, tout, tout, e, M, N, K, sm_count, stream, dbg_mode);
+        case EPI_BIAS_GELU_F16: return launch_pair<EPI_BIAS_GELU_F16>(ta, tb, tout, tout, e, M, N, K, sm_count, stream, dbg_mode);
+        case EPI_BIAS_QGELU_F16: return launch_pair<EPI_BIAS_QGELU_F16>(ta, tb, tout, tout, e, M, N, K, sm_count, stream, dbg_mode);
         case EPI_BIAS_RES_SPLIT:
             if (tlo == nullptr || (e.stats_in != nullptr && (e.ln_gamma == nullptr || e.ln_beta == nullptr))) return cudaErrorInvalidValue;
             if (e.stats_out != nullptr && e.stats_out == e.stats_in) return cudaErrorInvalidValue;

@@ -11,6 +11,7 @@ enum GemmEpilogue : int {
     EPI_BIAS_F16 = 0,       // out fp16 = LNfold(acc) + bias                     (fused QKV projection)
     EPI_BIAS_GELU_F16 = 1,  // out fp16 = gelu_erf(LNfold(acc) + bias)           (FFN up-projection)
     EPI_BIAS_RES_SPLIT = 2, // y (fp16 hi + fp16 lo, in place) = acc + bias + LN(y)  (attention-out / FFN down) + row statistics
+    EPI_BIAS_QGELU_F16 = 3, // out fp16 = quick_gelu(LNfold(acc) + bias), x * sigmoid(1.702 x)   (CLIP MLP up-projection)
 };
 
 constexpr int HIDDEN = 768;
@@ -74,6 +75,15 @@ cudaError_t launch_ln_materialize(const __half* yhi, const __half* ylo, const fl
 // where `out` may be a peer-mapped pointer into the root GPU's gather buffer (the fused gather).
 cudaError_t launch_pool_normalize(const __half* yhi, const __half* ylo, const float* gamma, const float* beta, float* out,
                                   int n_items, int S, float eps, cudaStream_t stream);
+
+// ViT image tower (CLIP): pixels fp32 [n, 3, img, img] -> im2col A fp16 [n*T, 3 p p] (class-token rows zero); patch GEMM output +
+// class / position embeddings + pre_layrnorm -> residual stream + statistics; pooled head: post_layernorm(class token) ->
+// projection [P, 768] -> L2 normalise, stored at out + i * P (possibly peer memory).
+cudaError_t launch_im2col(const float* pixels, __half* a, int n_items, int img, int p, cudaStream_t stream);
+cudaError_t launch_vit_embed(const __half* patch_out, const float* cls, const float* pos, const float* gamma, const float* beta,
+                             __half* yhi, __half* ylo, float2* stats, int n_rows, int T, float eps, cudaStream_t stream);
+cudaError_t launch_vit_pool(const __half* yhi, const __half* ylo, const float* gamma, const float* beta, const float* proj, float* out,
+                            int n_items, int T, int P, float eps, cudaStream_t stream);
 
 // fp32 -> fp16 (weight conversion at model load)
 cudaError_t launch_f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t stream);

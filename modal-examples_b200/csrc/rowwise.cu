@@ -143,6 +143,116 @@ pool_normalize_kernel(const __half* __restrict__ yhi, const __half* __restrict__
         o4[i * 32 + lane] = make_float4(x[i].x * inv, x[i].y * inv, x[i].z * inv, x[i].w * inv);
 }
 
+// ----------------------------------------------------------------------------------------------- ViT image tower (CLIP)
+// Restates CLIPVisionEmbeddings.forward / the pooled head of CLIPVisionTransformer + visual_projection (HF modeling_clip.py)
+// for the reference's image-embedding example (06_gpu_and_ml/embeddings/image_embeddings_infinity.py:76-77, 298-306).
+
+// pixels fp32 [B, 3, img, img] -> A fp16 [B * T, 3 p p], T = (img/p)^2 + 1: row b*T is zero (the class token takes no patch),
+// row b*T + 1 + (py*grid + px) holds patch (py, px) flattened (channel, row, column) -- the stride-p convolution as a GEMM.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+im2col_kernel(const float* __restrict__ pixels, __half* __restrict__ a, int n_rows, int img, int p, int grid) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int T = grid * grid + 1, pd = 3 * p * p;
+    const int b = row / T, tk = row % T;
+    __half2* o = reinterpret_cast<__half2*>(a + static_cast<size_t>(row) * pd);
+    if (tk == 0) {
+        for (int e = lane; e < pd / 2; e += 32) o[e] = __floats2half2_rn(0.f, 0.f);
+        return;
+    }
+    const int py = (tk - 1) / grid, px = (tk - 1) % grid;
+    const float* base = pixels + static_cast<size_t>(b) * 3 * img * img + static_cast<size_t>(py * p) * img + px * p;
+    for (int e = lane * 2; e < pd; e += 64) {
+        const int c = e / (p * p), ky = (e / p) % p, kx = e % p;  // kx even: the pair stays inside one patch row
+        const float2 v = *reinterpret_cast<const float2*>(base + (static_cast<size_t>(c) * img + ky) * img + kx);
+        o[e / 2] = __floats2half2_rn(v.x, v.y);
+    }
+}
+
+// row b*T + tk: e = (tk == 0 ? class_embedding : patch GEMM output) + position[tk]; h = pre_layrnorm(e) becomes the residual
+// stream (hi + lo) together with its (sum, M2) partials -- the statistics LayerNorm1 of the first layer folds.
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+vit_embed_kernel(const __half* __restrict__ patch_out, const float* __restrict__ cls, const float* __restrict__ pos,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ yhi, __half* __restrict__ ylo,
+                 float2* __restrict__ stats, int n_rows, int T, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int tk = row % T;
+    const uint2* p2 = reinterpret_cast<const uint2*>(patch_out + static_cast<size_t>(row) * H);
+    const float4* c4 = reinterpret_cast<const float4*>(cls);
+    const float4* q4 = reinterpret_cast<const float4*>(pos + static_cast<size_t>(tk) * H);
+    float4 x[V4];
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        float4 v;
+        if (tk == 0) {
+            v = __ldg(c4 + i * 32 + lane);
+        } else {
+            const uint2 hv = p2[i * 32 + lane];
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hv.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&hv.y));
+            v = make_float4(a.x, a.y, b.x, b.y);
+        }
+        const float4 q = __ldg(q4 + i * 32 + lane);
+        x[i] = make_float4(v.x + q.x, v.y + q.y, v.z + q.z, v.w + q.w);
+    }
+    ln_inplace(x, gamma, beta, eps, lane);
+    uint2* oh = reinterpret_cast<uint2*>(yhi + static_cast<size_t>(row) * H);
+    uint2* ol = reinterpret_cast<uint2*>(ylo + static_cast<size_t>(row) * H);
+    float ps = 0.f, pq = 0.f;
+#pragma unroll
+    for (int i = 0; i < V4; ++i) {
+        const float4 v = x[i];
+        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        oh[i * 32 + lane] = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        ol[i * 32 + lane] = make_uint2(pack_half2(v.x - f0.x, v.y - f0.y), pack_half2(v.z - f1.x, v.w - f1.y));
+        const float sm = warp_sum((v.x + v.y) + (v.z + v.w));
+        const float m = sm * (1.0f / 128.0f);
+        const float dx = v.x - m, dy = v.y - m, dz = v.z - m, dw = v.w - m;
+        const float q = warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw));
+        if (lane == i) { ps = sm; pq = q; }
+    }
+    if (lane < STAT_PARTS) stats[static_cast<size_t>(row) * STAT_PARTS + lane] = make_float2(ps, pq);
+}
+
+// One block per image: post_layernorm of the class-token row, visual projection [P, H], L2 normalise; row i is stored at
+// out + i * P, possibly peer memory (the fused gather).
+constexpr int VIT_POOL_MAX_P = 1024;
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+vit_pool_kernel(const __half* __restrict__ yhi, const __half* __restrict__ ylo, const float* __restrict__ gamma,
+                const float* __restrict__ beta, const float* __restrict__ proj, float* __restrict__ out, int T, int P, float eps) {
+    __shared__ float s_out[VIT_POOL_MAX_P];
+    __shared__ float s_red[WARPS_PER_BLOCK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int item = blockIdx.x;
+    float4 x[V4];
+    load_split_row(yhi, ylo, static_cast<size_t>(item) * T, lane, x);  // class-token row (every warp keeps its own copy)
+    ln_inplace(x, gamma, beta, eps, lane);
+    float sq = 0.f;
+    for (int n = warp; n < P; n += WARPS_PER_BLOCK) {
+        const float4* w4 = reinterpret_cast<const float4*>(proj + static_cast<size_t>(n) * H);
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < V4; ++i) {
+            const float4 w = __ldg(w4 + i * 32 + lane);
+            acc = fmaf(x[i].x, w.x, fmaf(x[i].y, w.y, fmaf(x[i].z, w.z, fmaf(x[i].w, w.w, acc))));
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) s_out[n] = acc;
+        sq = fmaf(acc, acc, sq);  // identical on every lane after warp_sum
+    }
+    if (lane == 0) s_red[warp] = sq;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS_PER_BLOCK; ++w) tot += s_red[w];
+    const float inv = 1.0f / fmaxf(sqrtf(tot), 1e-12f);
+    float* o = out + static_cast<size_t>(item) * P;
+    for (int n = threadIdx.x; n < P; n += WARPS_PER_BLOCK * 32) o[n] = s_out[n] * inv;
+}
+
 // Load-time weight preparation, one warp per output row n of W[N,K] (see kernels.h, "LNfold"):
 //   gamma given: w_out[n,k] = fp16(w[n,k] gamma[k] - m_n),  m_n = mean_k(w[n,k] gamma[k])   (rows centred: the LayerNorm's mean
 //                subtraction then happens inside the GEMM),  cvec[n] = sum_k w[n,k] beta[k] + bias[n]
@@ -226,6 +336,28 @@ cudaError_t launch_pool_normalize(const __half* yhi, const __half* ylo, const fl
                                   int n_items, int S, float eps, cudaStream_t stream) {
     const int grid = (n_items + rw::WARPS_PER_BLOCK - 1) / rw::WARPS_PER_BLOCK;
     rw::pool_normalize_kernel<<<grid, rw::WARPS_PER_BLOCK * 32, 0, stream>>>(yhi, ylo, gamma, beta, out, n_items, S, eps);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_im2col(const float* pixels, __half* a, int n_items, int img, int p, cudaStream_t stream) {
+    const int grid_sz = img / p, T = grid_sz * grid_sz + 1;
+    if (img % p != 0 || (3 * p * p) % 64 != 0 || p % 2 != 0) return cudaErrorInvalidValue;
+    const int rows = n_items * T;
+    rw::im2col_kernel<<<(rows + rw::WARPS_PER_BLOCK - 1) / rw::WARPS_PER_BLOCK, rw::WARPS_PER_BLOCK * 32, 0, stream>>>(pixels, a, rows, img, p, grid_sz);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_vit_embed(const __half* patch_out, const float* cls, const float* pos, const float* gamma, const float* beta,
+                             __half* yhi, __half* ylo, float2* stats, int n_rows, int T, float eps, cudaStream_t stream) {
+    rw::vit_embed_kernel<<<(n_rows + rw::WARPS_PER_BLOCK - 1) / rw::WARPS_PER_BLOCK, rw::WARPS_PER_BLOCK * 32, 0, stream>>>(
+        patch_out, cls, pos, gamma, beta, yhi, ylo, stats, n_rows, T, eps);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_vit_pool(const __half* yhi, const __half* ylo, const float* gamma, const float* beta, const float* proj, float* out,
+                            int n_items, int T, int P, float eps, cudaStream_t stream) {
+    if (P < 1 || P > rw::VIT_POOL_MAX_P) return cudaErrorInvalidValue;
+    rw::vit_pool_kernel<<<n_items, rw::WARPS_PER_BLOCK * 32, 0, stream>>>(yhi, ylo, gamma, beta, proj, out, T, P, eps);
     return cudaGetLastError();
 }
 
