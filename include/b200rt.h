@@ -33,6 +33,13 @@ typedef struct b200rt_bert_config {
     float eps;
 } b200rt_bert_config;
 
+/* Geometry of a CLIP-style ViT image tower (HF CLIPVisionConfig fields + projection_dim).  The kernels are specialised for
+ * ViT-B/16: hidden 768, 12 heads of 64, inter 3072, (image/patch)^2 + 1 <= 512 tokens, 3*patch*patch a multiple of 64. */
+typedef struct b200rt_vit_config {
+    int32_t image, patch, hidden, layers, heads, inter, proj;
+    float eps;
+} b200rt_vit_config;
+
 typedef struct b200rt_stats_t {
     uint64_t items, waves, tickets;     /* completed so far */
     uint64_t kernel_launches;           /* of this library's own kernels */
@@ -54,7 +61,9 @@ int b200rt_num_gpus(void);
 
 /* Cold start.  Stands in for `download_model` / `spawn_server` (text_embeddings_inference.py:37-56):
  * one host->root-GPU copy of the fp32 weight blob, fp16 conversion on the GPU, then a peer broadcast
- * over NVLink to the other replicas.  kind = "bert".  Blob order: see DESIGN.md / oracle blob_layout. */
+ * over NVLink to the other replicas.  kind = "bert" (cfg: b200rt_bert_config; blob order: b200rt.weights.blob_layout) or
+ * "vit" (cfg: b200rt_vit_config; the CLIP ViT-B/16 image tower behind 06_gpu_and_ml/embeddings/image_embeddings_infinity.py:76-77;
+ * blob order: b200rt.weights.vit_blob_layout).                                                         */
 int b200rt_model_load(const char* kind, const void* cfg, const void* weights, size_t nbytes, int* model_out);
 
 /* One .map() input.  Stands in for `TextEmbeddingsInference.embed` -> `POST /embed`
@@ -71,6 +80,12 @@ int b200rt_submit(int model, const int32_t* ids, const int32_t* lens, int n_item
 #define B200RT_SUBMIT_BORROW_IDS 1u
 int b200rt_submit_ex(int model, const int32_t* ids, const int32_t* lens, int n_items, int max_len, float* out,
                      uint32_t flags, uint64_t* ticket_out);
+/* One .map() input of the image example (image_embeddings_infinity.py:330-350, `engine.image_embed(images=...)`), with
+ * preprocessed pixels instead of image paths: pixels is [n_items, 3, image, image] fp32 (resized / normalised as CLIP's
+ * processor does), out receives [n_items, proj] fp32 unit-norm embeddings.  Both stay caller-owned and must remain valid until
+ * the ticket completes; each replica pulls its share of the pixels over its own PCIe link (no scatter through the root:
+ * an image is 600 KB, not 2 KB).  Pinned memory (b200rt_alloc_pinned) makes the copies asynchronous.  model: kind "vit". */
+int b200rt_submit_pixels(int model, const float* pixels, int n_items, float* out, uint64_t* ticket_out);
 /* Completion, ordered (`order_outputs=True`): a ticket being waited on is never handed to b200rt_poll_any ...  */
 int b200rt_wait(uint64_t ticket, int timeout_ms); /* timeout_ms < 0: forever */
 /* ... and unordered (`order_outputs=False`, text_embeddings_inference.py:167): next finished ticket

@@ -33,6 +33,10 @@ int b200rt_debug_attention(const uint16_t* qkv, const int32_t* lens, uint16_t* c
 int b200rt_debug_hidden(int model, const int32_t* ids, const int32_t* lens, int n_items, int max_len, int n_layers,
                         float* hidden_out);
 
+/* ViT model: the residual stream after `n_layers` encoder layers (0 = pre_layrnorm output) for pixels [n_items, 3, image,
+ * image], hidden_out fp32 [n_items * tokens, hidden] on the host (pre-LN architecture: the stream itself, not a LayerNorm of it). */
+int b200rt_debug_vit_hidden(int model, const float* pixels, int n_items, int n_layers, float* hidden_out);
+
 /* Per-kernel device times (ms, CUDA events on the compute stream) of one forward of a resident batch:
  * names_out receives up to cap NUL-terminated names packed in a char buffer, ms_out the times.        */
 int b200rt_debug_profile_forward(int model, int n_items, int max_len, int iters, char* names_out, size_t names_cap,

@@ -24,11 +24,11 @@ E_INVALID, E_STATE, E_CUDA, E_NOMEM, E_UNSUPPORTED = -1, -2, -3, -4, -5
 
 # every symbol include/b200rt.h and include/b200rt_debug.h declare (tests check the export list)
 ABI_SYMBOLS = [
-    "b200rt_init", "b200rt_init_devices", "b200rt_num_gpus", "b200rt_model_load", "b200rt_submit", "b200rt_submit_ex", "b200rt_wait",
+    "b200rt_init", "b200rt_init_devices", "b200rt_num_gpus", "b200rt_model_load", "b200rt_submit", "b200rt_submit_ex", "b200rt_submit_pixels", "b200rt_wait",
     "b200rt_poll_any", "b200rt_embed_device", "b200rt_device_sync", "b200rt_wave_capacity_items",
     "b200rt_alloc_pinned", "b200rt_free_pinned", "b200rt_stats", "b200rt_last_error", "b200rt_shutdown",
 ]
-DEBUG_SYMBOLS = ["b200rt_debug_gemm", "b200rt_debug_attention", "b200rt_debug_hidden", "b200rt_debug_profile_forward"]
+DEBUG_SYMBOLS = ["b200rt_debug_gemm", "b200rt_debug_attention", "b200rt_debug_hidden", "b200rt_debug_vit_hidden", "b200rt_debug_profile_forward"]
 
 
 class B200RTError(RuntimeError):
@@ -41,6 +41,10 @@ class BertConfig(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("vocab", "hidden", "layers", "heads", "inter", "max_pos", "type_vocab")] + [
         ("eps", ctypes.c_float)
     ]
+
+
+class VitConfig(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("image", "patch", "hidden", "layers", "heads", "inter", "proj")] + [("eps", ctypes.c_float)]
 
 
 class Stats(ctypes.Structure):
@@ -76,6 +80,8 @@ def load_library():
         lib.b200rt_submit.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, u64p]
         lib.b200rt_submit_ex.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
                                          ctypes.c_uint32, u64p]
+        lib.b200rt_submit_pixels.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, u64p]
+        lib.b200rt_debug_vit_hidden.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
         lib.b200rt_wait.argtypes = [ctypes.c_uint64, ctypes.c_int]
         lib.b200rt_poll_any.argtypes = [u64p, ctypes.c_int]
         lib.b200rt_embed_device.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
@@ -293,6 +299,56 @@ class EmbedModel:
         _check(self._lib.b200rt_debug_profile_forward(self.handle, n_items, max_len, iters, names, 4096, ms, ctypes.byref(n), 64))
         parts = names.raw.split(b"\0")
         return {parts[i].decode(): float(ms[i]) for i in range(n.value)}
+
+
+class ImageEmbedModel:
+    """A loaded CLIP-style ViT image tower (kind "vit"): ``submit``/``wait`` take preprocessed pixels
+    ``[n, 3, image, image]`` float32 and give ``[n, proj]`` unit-norm embeddings -- the in-box stand-in for
+    ``engine.image_embed(images=...)`` in the reference's image example (image_embeddings_infinity.py:330-350)."""
+
+    def __init__(self, geometry: dict, blob: np.ndarray):
+        lib = load_library()
+        blob = np.ascontiguousarray(blob, dtype=np.float32)
+        g = geometry
+        self.cfg = VitConfig(g["image"], g["patch"], g["hidden"], g["layers"], g["heads"], g["inter"], g["proj"], g["eps"])
+        self.image, self.proj = g["image"], g["proj"]
+        self.tokens = (g["image"] // g["patch"]) ** 2 + 1
+        self.hidden = g["hidden"]
+        h = ctypes.c_int32(-1)
+        _check(lib.b200rt_model_load(b"vit", ctypes.byref(self.cfg), _ptr(blob), blob.nbytes, ctypes.byref(h)))
+        self.handle = h.value
+        self._lib = lib
+
+    def submit(self, pixels: np.ndarray, out: np.ndarray | None = None, tag=None) -> Ticket:
+        """``pixels`` (C-contiguous float32) and ``out`` stay lent to the library until the ticket completes."""
+        if not (isinstance(pixels, np.ndarray) and pixels.dtype == np.float32 and pixels.flags.c_contiguous):
+            pixels = np.ascontiguousarray(pixels, dtype=np.float32)
+        if pixels.ndim != 4 or pixels.shape[1:] != (3, self.image, self.image):
+            raise B200RTError(E_INVALID, f"pixels must be [n, 3, {self.image}, {self.image}], got shape {pixels.shape}")
+        n = pixels.shape[0]
+        if out is None:
+            out = np.empty((n, self.proj), np.float32)
+        elif out.dtype != np.float32 or not out.flags.c_contiguous or out.shape != (n, self.proj):
+            raise B200RTError(E_INVALID, "out must be a C-contiguous float32 [n_items, proj] array")
+        t = ctypes.c_uint64(0)
+        with _live_lock:
+            _check(self._lib.b200rt_submit_pixels(self.handle, _ptr(pixels), n, _ptr(out), ctypes.byref(t)))
+            tk = Ticket(t.value, out, tag, pixels)
+            _live[tk.id] = tk
+        return tk
+
+    wait = EmbedModel.wait
+    poll_any = EmbedModel.poll_any
+
+    def embed(self, pixels: np.ndarray) -> np.ndarray:
+        return self.wait(self.submit(pixels))
+
+    def debug_hidden(self, pixels: np.ndarray, n_layers: int) -> np.ndarray:
+        pixels = np.ascontiguousarray(pixels, dtype=np.float32)
+        n = pixels.shape[0]
+        out = np.empty((n * self.tokens, self.hidden), np.float32)
+        _check(self._lib.b200rt_debug_vit_hidden(self.handle, _ptr(pixels), n, n_layers, _ptr(out)))
+        return out.reshape(n, self.tokens, self.hidden)
 
 
 def device_sync(gpu: int = 0):

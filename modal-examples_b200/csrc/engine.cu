@@ -132,6 +132,7 @@ int make_map_qkv(CUtensorMap* m, const void* base, uint64_t B, uint64_t S, uint6
 constexpr int NSLOT = 4;
 constexpr int MIN_ITEMS_PER_REPLICA = 8;  // a wave uses fewer replicas rather than giving one fewer items than this
 constexpr int MAX_SEQ = 512;
+constexpr int VIT_WAVE_ITEMS = 64;  // images one replica takes per wave (64 x 197 tokens; 38.5 MB of pixels per wave slot)
 
 struct LayerW {
     __half *qkv_w, *ao_w, *ff1_w, *ff2_w;
@@ -147,10 +148,23 @@ struct DevWeights {
     __half* f16_arena = nullptr; // GEMM weights
     float *word, *pos, *type, *emb_g, *emb_b;
     std::vector<LayerW> layers;
+    // ViT (kind "vit"): patch projection (fp16, the stride-p convolution as a [H, 3 p p] matrix), class / position embeddings,
+    // pre / post LayerNorm, visual projection; `pos` above holds the position table.  For a ViT layer, LayerW::ln1_* is the
+    // LayerNorm folded into QKV and ln2_* the one folded into FFN1 (pre-LN: neither is re-applied to the residual).
+    __half* patch_w = nullptr;
+    CUtensorMap m_patch;
+    float *cls = nullptr, *pre_g = nullptr, *pre_b = nullptr, *post_g = nullptr, *post_b = nullptr, *proj_w = nullptr, *zero_bias = nullptr;
 };
 
+enum ModelKind { KIND_BERT = 0, KIND_VIT = 1 };
+
 struct Model {
-    b200rt_bert_config cfg;
+    ModelKind kind = KIND_BERT;
+    b200rt_bert_config cfg{};
+    b200rt_vit_config vcfg{};
+    int tokens = 0;          // vit: (image / patch)^2 + 1
+    int out_dim = HIDDEN;    // floats per item in the result
+    size_t item_bytes = 0;   // vit: bytes of one item's pixels
     size_t f32_elems = 0, f16_elems = 0;
     std::vector<DevWeights> per_dev;
 };
@@ -171,6 +185,11 @@ struct Dev {
     // wave input slots (written by the root's scatter kernel, possibly over NVLink)
     int32_t* ids_in[NSLOT] = {};
     int32_t* lens_in[NSLOT] = {};
+    float* pix_in[NSLOT] = {};     // vit: this replica's share of a wave's pixels (allocated when the first vit model loads)
+    cudaStream_t copy = nullptr;   // vit: H2D of wave k+1's pixels runs here, under the forward of wave k on `compute`
+    cudaEvent_t ev_pix[NSLOT] = {};
+    int32_t* lens_const = nullptr; // vit: every item has `tokens` keys
+    CUtensorMap m_im2col;          // vit: the ffn buffer viewed as the im2col matrix [rows, 768]
     cudaEvent_t ev_done[NSLOT];
     cudaEvent_t ev_begin[NSLOT], ev_end[NSLOT];  // timing: the forward itself on this replica's compute stream
     std::mutex mu;  // serialises host-side enqueue on this replica (scheduler vs. embed_device/debug)
@@ -195,6 +214,7 @@ struct Ticket {
     const Model* mp = nullptr;  // resolved at submit time (the models vector may grow while the ticket is queued)
     std::vector<int32_t> ids;   // private copy [n, S] (empty when the caller lent us its buffer: `borrowed`)
     const int32_t* ids_ext = nullptr;
+    const float* pixels = nullptr;  // vit tickets: [n_items, 3, image, image] fp32, caller-owned until completion
     bool borrowed = false, ids_pinned = false, out_pinned = false;
     const int32_t* ids_ptr() const { return borrowed ? ids_ext : ids.data(); }
     std::vector<int32_t> lens;
@@ -228,6 +248,7 @@ struct Wave {
     int n_items, S;
     int first_dev = 0;        // lowest replica that took part (its events time the forward)
     bool direct_h2d = false;  // some segments were DMA'd from caller-pinned memory
+    int out_dim = HIDDEN;     // floats per result row
     std::vector<Segment> segs;
 };
 
@@ -252,6 +273,7 @@ struct Runtime {
     std::deque<Wave> inflight;
     bool slot_busy[NSLOT] = {};
     int fill_window_us = 200;
+    size_t vit_item_bytes = 0;  // bytes of one image of the loaded vit model(s)
     std::chrono::steady_clock::time_point last_submit = std::chrono::steady_clock::now();
     int active_calls = 0;  // threads inside b200rt_wait / b200rt_poll_any (shutdown waits for them to leave)
     uint64_t next_ticket = 1, next_wave = 0;
@@ -346,6 +368,58 @@ int forward_enqueue(Dev& d, const Model& m, int dev_index, const int32_t* ids, c
         ++nl;
     }
     if (launches) *launches += nl;
+    return 0;
+}
+
+// Forward of one batch of images on `stream`: pixels fp32 [B, 3, image, image] in this replica's HBM; out fp32 [B, proj],
+// may be peer memory.  n_layers >= 0 (debug): stop after that many layers (the residual stream stays in yhi / ylo).
+// CLIPVisionTransformer is pre-LN: LayerNorm1 / LayerNorm2 are folded into QKV / FFN1, the residual GEMMs add the raw
+// stream (no LayerNorm re-applied) and emit the statistics the next fold needs.
+int forward_enqueue_vit(Dev& d, const Model& m, int dev_index, const float* pixels, int B, float* out, cudaStream_t stream,
+                        int n_layers = -1, uint64_t* launches = nullptr) {
+    const DevWeights& w = m.per_dev[dev_index];
+    const b200rt_vit_config& c = m.vcfg;
+    const int T = m.tokens, M = B * T;
+    const int L = n_layers < 0 ? c.layers : n_layers;
+    if (M > g_rt->cap_rows || B > VIT_WAVE_ITEMS) return fail(B200RT_E_INVALID, "batch of %d images exceeds the wave capacity (%d)", B, VIT_WAVE_ITEMS);
+    const CUtensorMap *mq = nullptr, *mc = nullptr;
+    if (int rc = get_qkv_map(d, T, &mq, &mc)) return rc;
+    uint64_t nl = 0;
+    // patches -> im2col rows in the (idle) ffn buffer -> patch projection into the (idle) ctx buffer -> + class / position
+    // embeddings, pre_layrnorm -> residual stream + statistics
+    CUDA_TRY(launch_im2col(pixels, d.ffn, B, c.image, c.patch, stream));
+    GemmEpi e_patch{w.zero_bias, nullptr, STAT_PARTS, nullptr, nullptr, nullptr, c.eps};
+    CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_im2col, w.m_patch, d.m_ctx, nullptr, e_patch, M, HIDDEN, 3 * c.patch * c.patch, d.sm_count, stream));
+    CUDA_TRY(launch_vit_embed(d.ctx, w.cls, w.pos, w.pre_g, w.pre_b, d.yhi, d.ylo, d.pstats[0], M, T, c.eps, stream));
+    nl += 3;
+    for (int l = 0; l < L; ++l) {
+        const LayerW& lw = w.layers[l];
+        GemmEpi e_qkv{lw.qkv_c, d.pstats[0], STAT_PARTS, nullptr, nullptr, nullptr, c.eps};
+        CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_yhi, lw.m_qkv, d.m_qkv2d, nullptr, e_qkv, M, QKV_DIM, HIDDEN, d.sm_count, stream));
+        CUDA_TRY(launch_attention(*mq, *mc, d.lens_const, B, T, d.sm_count, stream));
+        GemmEpi e_ao{lw.ao_b, nullptr, STAT_PARTS, nullptr, nullptr, d.pstats[1], c.eps};  // h += ctx Wo^T + b (raw residual)
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_SPLIT, d.m_ctx, lw.m_ao, d.m_yhi_c, &d.m_ylo_c, e_ao, M, HIDDEN, HIDDEN, d.sm_count, stream));
+        GemmEpi e_ff1{lw.ff1_c, d.pstats[1], STAT_PARTS, nullptr, nullptr, nullptr, c.eps};
+        CUDA_TRY(launch_gemm(EPI_BIAS_QGELU_F16, d.m_yhi, lw.m_ff1, d.m_ffn, nullptr, e_ff1, M, c.inter, HIDDEN, d.sm_count, stream));
+        GemmEpi e_ff2{lw.ff2_b, nullptr, STAT_PARTS, nullptr, nullptr, d.pstats[0], c.eps};
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_SPLIT, d.m_ffn, lw.m_ff2, d.m_yhi_c, &d.m_ylo_c, e_ff2, M, HIDDEN, c.inter, d.sm_count, stream));
+        nl += 5;
+    }
+    if (n_layers < 0) {
+        CUDA_TRY(launch_vit_pool(d.yhi, d.ylo, w.post_g, w.post_b, w.proj_w, out, B, T, c.proj, c.eps, stream));
+        ++nl;
+    }
+    if (launches) *launches += nl;
+    return 0;
+}
+
+// Orders a ViT forward behind the previous forward on the replica's workspace, like forward() does (caller holds d.mu).
+int forward_vit(Dev& d, const Model& m, int dev_index, const float* pixels, int B, float* out, cudaStream_t stream, int n_layers = -1,
+                uint64_t* launches = nullptr) {
+    if (d.ev_ws_armed) CUDA_TRY(cudaStreamWaitEvent(stream, d.ev_ws, 0));
+    if (int rc = forward_enqueue_vit(d, m, dev_index, pixels, B, out, stream, n_layers, launches)) return rc;
+    CUDA_TRY(cudaEventRecord(d.ev_ws, stream));
+    d.ev_ws_armed = true;
     return 0;
 }
 
@@ -523,7 +597,7 @@ void dispatcher_main(Runtime* rtp) {
             {
                 const int S0 = rt.pending.front().bucket;
                 const Model* m0 = rt.pending.front().t->mp;
-                const int cap0 = (rt.cap_rows / S0) * G;
+                const int cap0 = (m0->kind == KIND_VIT ? VIT_WAVE_ITEMS : rt.cap_rows / S0) * G;
                 auto queued = [&] {
                     int n = 0;
                     for (auto& r : rt.pending)
@@ -550,7 +624,7 @@ void dispatcher_main(Runtime* rtp) {
             wv.n_items = 0;
             const Model* model = rt.pending.front().t->mp;
             // token capacity scales with 512/S: a wave holds cap_rows tokens per replica
-            const int cap_items_S = (rt.cap_rows / wv.S) * G;
+            const int cap_items_S = (model->kind == KIND_VIT ? VIT_WAVE_ITEMS : rt.cap_rows / wv.S) * G;
             for (auto it = rt.pending.begin(); it != rt.pending.end() && wv.n_items < cap_items_S;) {
                 if (it->bucket != wv.S || it->t->mp != model) {
                     ++it;
@@ -571,12 +645,15 @@ void dispatcher_main(Runtime* rtp) {
         // Stage the wave's ids on the root GPU.  A segment whose ids the caller lent us in pinned memory, at the
         // wave's own padded length, is DMA'd from where it lies; anything else goes through the slot's pinned buffer
         // (re-strided to the bucket length when the ticket's max_len is shorter).
+        const bool vit = model.kind == KIND_VIT;
+        const int out_dim = model.out_dim;
         bool staged = false;
         auto direct_ids = [&](const Segment& sg) {  // lent, pinned, already at the wave's padded length, items in place
             const Ticket& t = *sg.t;
             return t.borrowed && t.ids_pinned && t.S == S && t.order.empty();
         };
         for (const Segment& sg : wv.segs) {
+            if (vit) break;  // image payloads are pulled by each replica itself (below): nothing is staged on the root
             const Ticket& t = *sg.t;
             int32_t* hdst = rt.h_ids[slot] + static_cast<size_t>(sg.wave_off) * S;
             if (direct_ids(sg)) {
@@ -598,8 +675,9 @@ void dispatcher_main(Runtime* rtp) {
                 }
             }
         }
-        for (const Segment& sg : wv.segs)
-            for (int i = 0; i < sg.count; ++i) rt.h_lens[slot][sg.wave_off + i] = sg.t->lens[sg.t->item_at(sg.ticket_off + i)];
+        if (!vit)
+            for (const Segment& sg : wv.segs)
+                for (int i = 0; i < sg.count; ++i) rt.h_lens[slot][sg.wave_off + i] = sg.t->lens[sg.t->item_at(sg.ticket_off + i)];
         auto t_host1 = std::chrono::steady_clock::now();
         if (staged) {
             if (!wv.direct_h2d) {
@@ -614,8 +692,9 @@ void dispatcher_main(Runtime* rtp) {
                 }
             }
         }
-        SCHED_TRY(cudaMemcpyAsync(rt.d_lens_stage[slot], rt.h_lens[slot], static_cast<size_t>(n) * 4,
-                                  cudaMemcpyHostToDevice, rt.s_in));
+        if (!vit)
+            SCHED_TRY(cudaMemcpyAsync(rt.d_lens_stage[slot], rt.h_lens[slot], static_cast<size_t>(n) * 4,
+                                      cudaMemcpyHostToDevice, rt.s_in));
         // Replicas used by this wave: everyone when there is enough work, otherwise as many as get at least
         // MIN_ITEMS_PER_REPLICA items each, starting from a rotating replica so that consecutive small waves land on
         // different GPUs.  Contiguous item ranges, as even as possible.
@@ -638,9 +717,9 @@ void dispatcher_main(Runtime* rtp) {
             const int b0 = std::min(n, k * per), b1 = std::min(n, (k + 1) * per);
             plan.item_begin[g] = b0;
             plan.item_count[g] = b1 - b0;
-            if (g != 0) peer_bytes += static_cast<uint64_t>(b1 - b0) * (S * 4 + 4 + HIDDEN * 4);
+            if (g != 0) peer_bytes += static_cast<uint64_t>(b1 - b0) * (vit ? out_dim * 4 : S * 4 + 4 + out_dim * 4);
         }
-        SCHED_TRY(launch_scatter(rt.d_ids_stage[slot], rt.d_lens_stage[slot], plan, rt.s_in));
+        if (!vit) SCHED_TRY(launch_scatter(rt.d_ids_stage[slot], rt.d_lens_stage[slot], plan, rt.s_in));
         SCHED_TRY(cudaEventRecord(rt.ev_scatter[slot], rt.s_in));
         // every participating replica's launcher thread enqueues its own forward (~85 launches each, in parallel)
         std::atomic<uint64_t> launches{1};
@@ -667,10 +746,27 @@ void dispatcher_main(Runtime* rtp) {
                 {
                     std::lock_guard<std::mutex> dl(dd.mu);
                     uint64_t nl = 0;
-                    float* dst = rt.d_out_gather[slot] + static_cast<size_t>(plan.item_begin[g]) * HIDDEN;
+                    float* dst = rt.d_out_gather[slot] + static_cast<size_t>(plan.item_begin[g]) * out_dim;
                     if (ck(cudaStreamWaitEvent(dd.compute, rt.ev_scatter[slot], 0), "cudaStreamWaitEvent") &&
                         ck(cudaEventRecord(dd.ev_begin[slot], dd.compute), "cudaEventRecord")) {
-                        int rc = forward(dd, model, g, dd.ids_in[slot], dd.lens_in[slot], plan.item_count[g], S, dst, dd.compute, -1, nullptr, &nl);
+                        int rc = 0;
+                        if (vit) {
+                            // this replica's items, segment by segment, straight from the callers' buffers over its own PCIe link
+                            const int b0 = plan.item_begin[g], b1 = b0 + plan.item_count[g];
+                            for (const Segment& sg : wv.segs) {
+                                const int lo = std::max(b0, sg.wave_off), hi = std::min(b1, sg.wave_off + sg.count);
+                                if (lo >= hi) continue;
+                                const float* src = sg.t->pixels + static_cast<size_t>(sg.ticket_off + (lo - sg.wave_off)) * (model.item_bytes / 4);
+                                if (!ck(cudaMemcpyAsync(dd.pix_in[slot] + static_cast<size_t>(lo - b0) * (model.item_bytes / 4), src,
+                                                        static_cast<size_t>(hi - lo) * model.item_bytes, cudaMemcpyHostToDevice, dd.copy), "cudaMemcpyAsync(pixels)"))
+                                    break;
+                            }
+                            if (e.empty() && ck(cudaEventRecord(dd.ev_pix[slot], dd.copy), "cudaEventRecord") &&
+                                ck(cudaStreamWaitEvent(dd.compute, dd.ev_pix[slot], 0), "cudaStreamWaitEvent"))
+                                rc = forward_vit(dd, model, g, dd.pix_in[slot], plan.item_count[g], dst, dd.compute, -1, &nl);
+                        } else {
+                            rc = forward(dd, model, g, dd.ids_in[slot], dd.lens_in[slot], plan.item_count[g], S, dst, dd.compute, -1, nullptr, &nl);
+                        }
                         if (rc) { e = t_last_error; code = rc; }
                         else {
                             ck(cudaEventRecord(dd.ev_end[slot], dd.compute), "cudaEventRecord");
@@ -709,23 +805,24 @@ void dispatcher_main(Runtime* rtp) {
         bool any_staged_out = false;
         for (const Segment& sg : wv.segs) {
             if (!(sg.t->out_pinned && sg.t->order.empty())) { any_staged_out = true; continue; }
-            SCHED_TRY(cudaMemcpyAsync(sg.t->out + static_cast<size_t>(sg.ticket_off) * HIDDEN,
-                                      rt.d_out_gather[slot] + static_cast<size_t>(sg.wave_off) * HIDDEN,
-                                      static_cast<size_t>(sg.count) * HIDDEN * 4, cudaMemcpyDeviceToHost, rt.s_out));
+            SCHED_TRY(cudaMemcpyAsync(sg.t->out + static_cast<size_t>(sg.ticket_off) * out_dim,
+                                      rt.d_out_gather[slot] + static_cast<size_t>(sg.wave_off) * out_dim,
+                                      static_cast<size_t>(sg.count) * out_dim * 4, cudaMemcpyDeviceToHost, rt.s_out));
         }
         if (any_staged_out)
-            SCHED_TRY(cudaMemcpyAsync(rt.h_out[slot], rt.d_out_gather[slot], static_cast<size_t>(n) * HIDDEN * 4,
+            SCHED_TRY(cudaMemcpyAsync(rt.h_out[slot], rt.d_out_gather[slot], static_cast<size_t>(n) * out_dim * 4,
                                       cudaMemcpyDeviceToHost, rt.s_out));
         SCHED_TRY(cudaEventRecord(rt.ev_wave[slot], rt.s_out));
         {
             std::lock_guard<std::mutex> sl(rt.stats_mu);
             rt.stats.kernel_launches += launches.load();
-            rt.stats.h2d_bytes += static_cast<uint64_t>(n) * (S * 4 + 4);
-            rt.stats.d2h_bytes += static_cast<uint64_t>(n) * HIDDEN * 4;
+            rt.stats.h2d_bytes += vit ? static_cast<uint64_t>(n) * model.item_bytes : static_cast<uint64_t>(n) * (S * 4 + 4);
+            rt.stats.d2h_bytes += static_cast<uint64_t>(n) * out_dim * 4;
             rt.stats.peer_bytes += peer_bytes;
             rt.stats.stage_us += std::chrono::duration<double, std::micro>(t_host1 - t_host0).count();
             rt.stats.dispatch_us += std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_host0).count();
         }
+        wv.out_dim = out_dim;
         {
             std::lock_guard<std::mutex> lk(rt.mu);
             rt.inflight.push_back(std::move(wv));
@@ -777,13 +874,14 @@ void completer_main(Runtime* rtp) {
                 for (const Segment& sg : wv.segs)
                     if (!sg.t->done && !(sg.t->out_pinned && sg.t->order.empty())) live.push_back(&sg);
             }
+            const size_t od = static_cast<size_t>(wv.out_dim);
             for (const Segment* sg : live) {
-                const float* src = rt.h_out[slot] + static_cast<size_t>(sg->wave_off) * HIDDEN;
+                const float* src = rt.h_out[slot] + static_cast<size_t>(sg->wave_off) * od;
                 if (sg->t->order.empty()) {
-                    memcpy(sg->t->out + static_cast<size_t>(sg->ticket_off) * HIDDEN, src, static_cast<size_t>(sg->count) * HIDDEN * 4);
+                    memcpy(sg->t->out + static_cast<size_t>(sg->ticket_off) * od, src, static_cast<size_t>(sg->count) * od * 4);
                 } else {  // rows go back to the items' own positions
                     for (int i = 0; i < sg->count; ++i)
-                        memcpy(sg->t->out + static_cast<size_t>(sg->t->order[sg->ticket_off + i]) * HIDDEN, src + static_cast<size_t>(i) * HIDDEN, HIDDEN * 4);
+                        memcpy(sg->t->out + static_cast<size_t>(sg->t->order[sg->ticket_off + i]) * od, src + static_cast<size_t>(i) * od, od * 4);
                 }
             }
         }
@@ -1036,6 +1134,150 @@ int model_load(const b200rt_bert_config& c, const float* blob, size_t nbytes, in
     return 0;
 }
 
+int model_load_vit(const b200rt_vit_config& c, const float* blob, size_t nbytes, int* model_out) {
+    Runtime& rt = *g_rt;
+    const int grid = c.patch > 0 ? c.image / c.patch : 0;
+    const int T = grid * grid + 1;
+    const size_t H = HIDDEN, I = 3072, PD = static_cast<size_t>(3) * c.patch * c.patch, P = static_cast<size_t>(c.proj);
+    if (c.hidden != HIDDEN || c.heads != HEADS || c.inter != 3072 || c.layers < 1 || c.patch < 2 || c.image % c.patch != 0 || T > MAX_SEQ ||
+        PD != HIDDEN || c.patch % 2 != 0 || c.proj < 1 || c.proj > 1024)
+        return fail(B200RT_E_UNSUPPORTED, "kernels are specialised for ViT-B: hidden=768 heads=12 inter=3072, <= 512 tokens, 3*patch^2 %% 64 == 0, proj <= 1024 "
+                                          "(got hidden %d heads %d inter %d image %d patch %d proj %d)", c.hidden, c.heads, c.inter, c.image, c.patch, c.proj);
+    const size_t per_layer_w = 3 * H * H + H * H + I * H + H * I;
+    const size_t per_layer_p = 2 * H + 3 * H + H + 2 * H + I + H;  // ln1, qkv.b, ao.b, ln2, ff1.b, ff2.b
+    const size_t head = H * PD + H + static_cast<size_t>(T) * H + 2 * H, tail = 2 * H + P * H;
+    const size_t total = head + static_cast<size_t>(c.layers) * (per_layer_w + per_layer_p) + tail;
+    if (nbytes != total * 4) return fail(B200RT_E_INVALID, "weight blob is %zu bytes, geometry needs %zu", nbytes, total * 4);
+
+    auto m = std::make_unique<Model>();
+    m->kind = KIND_VIT;
+    m->vcfg = c;
+    m->tokens = T;
+    m->out_dim = c.proj;
+    m->item_bytes = static_cast<size_t>(3) * c.image * c.image * 4;
+    const size_t per_layer_x = 3 * H + I;  // qkv_c, ff1_c
+    m->f32_elems = (head - H * PD) + static_cast<size_t>(c.layers) * (per_layer_p + per_layer_x) + tail + H /* zero bias */;
+    m->f16_elems = H * PD + static_cast<size_t>(c.layers) * per_layer_w;
+    m->per_dev.resize(rt.devs.size());
+
+    Dev& root = *rt.devs[0];
+    std::lock_guard<std::mutex> dl(root.mu);
+    CUDA_TRY(cudaSetDevice(root.id));
+    float* d_blob = nullptr;
+    CUDA_TRY(cudaMalloc(&d_blob, nbytes));
+    CUDA_TRY(cudaMemcpy(d_blob, blob, nbytes, cudaMemcpyHostToDevice));
+    for (size_t g = 0; g < rt.devs.size(); ++g) {
+        Dev& d = *rt.devs[g];
+        CUDA_TRY(cudaSetDevice(d.id));
+        CUDA_TRY(cudaMalloc(&m->per_dev[g].f32_arena, m->f32_elems * 4));
+        CUDA_TRY(cudaMalloc(&m->per_dev[g].f16_arena, m->f16_elems * 2));
+        // per-replica image input slots and constants, once
+        if (!d.lens_const) {
+            std::vector<int32_t> lens(VIT_WAVE_ITEMS, T);
+            CUDA_TRY(cudaMalloc(&d.lens_const, VIT_WAVE_ITEMS * 4));
+            CUDA_TRY(cudaMemcpy(d.lens_const, lens.data(), VIT_WAVE_ITEMS * 4, cudaMemcpyHostToDevice));
+            if (int rc = make_map_2d(&d.m_im2col, d.ffn, static_cast<uint64_t>(rt.cap_rows) * 4, HIDDEN, 128)) return rc;
+        }
+        if (!d.copy) CUDA_TRY(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
+        for (int sl = 0; sl < NSLOT; ++sl) {
+            if (!d.pix_in[sl]) CUDA_TRY(cudaMalloc(&d.pix_in[sl], VIT_WAVE_ITEMS * m->item_bytes));
+            if (!d.ev_pix[sl]) CUDA_TRY(cudaEventCreateWithFlags(&d.ev_pix[sl], cudaEventDisableTiming));
+        }
+    }
+    if (rt.vit_item_bytes != 0 && rt.vit_item_bytes != m->item_bytes)
+        return fail(B200RT_E_UNSUPPORTED, "a second vit model with a different image size is not supported in one runtime");
+    rt.vit_item_bytes = m->item_bytes;
+    CUDA_TRY(cudaSetDevice(root.id));
+    DevWeights& rw = m->per_dev[0];
+    {
+        size_t src = 0, o32 = 0, o16 = 0;
+        auto take32 = [&](size_t n) -> cudaError_t {
+            cudaError_t e = cudaMemcpyAsync(rw.f32_arena + o32, d_blob + src, n * 4, cudaMemcpyDeviceToDevice, root.compute);
+            src += n; o32 += n;
+            return e;
+        };
+        auto skip32 = [&](size_t n) { o32 += n; };  // derived vectors are written in place by the fold kernel
+        auto take16 = [&](size_t N_, size_t K_, const float* gamma, const float* beta, const float* bias, float* cv) -> cudaError_t {
+            cudaError_t e = launch_fold_ln(d_blob + src, gamma, beta, bias, rw.f16_arena + o16, cv, static_cast<int>(N_), static_cast<int>(K_), root.compute);
+            src += N_ * K_; o16 += N_ * K_;
+            return e;
+        };
+        CUDA_TRY(take16(H, PD, nullptr, nullptr, nullptr, nullptr));   // patch.w
+        CUDA_TRY(take32(H + static_cast<size_t>(T) * H + 2 * H));       // cls, pos, pre.g, pre.b
+        for (int l = 0; l < c.layers; ++l) {
+            const float* ln1_g = d_blob + src;
+            const float* ln1_b = d_blob + src + H;
+            CUDA_TRY(take32(2 * H));                                    // ln1.g, ln1.b
+            const float* qkv_b = d_blob + src + 3 * H * H;
+            float* qkv_c = rw.f32_arena + o32 + (3 * H) + H + 2 * H + I + H;  // after qkv.b ao.b ln2.g ln2.b ff1.b ff2.b
+            CUDA_TRY(take16(3 * H, H, ln1_g, ln1_b, qkv_b, qkv_c));     // qkv.w folded with ln1
+            CUDA_TRY(take32(3 * H));                                    // qkv.b
+            CUDA_TRY(take16(H, H, nullptr, nullptr, nullptr, nullptr)); // ao.w
+            CUDA_TRY(take32(H));                                        // ao.b
+            const float* ln2_g = d_blob + src;
+            const float* ln2_b = d_blob + src + H;
+            CUDA_TRY(take32(2 * H));                                    // ln2.g, ln2.b
+            const float* ff1_b = d_blob + src + I * H;
+            float* ff1_c = rw.f32_arena + o32 + I + H + 3 * H;          // after ff1.b ff2.b qkv_c
+            CUDA_TRY(take16(I, H, ln2_g, ln2_b, ff1_b, ff1_c));         // ff1.w folded with ln2
+            CUDA_TRY(take32(I));                                        // ff1.b
+            CUDA_TRY(take16(H, I, nullptr, nullptr, nullptr, nullptr)); // ff2.w
+            CUDA_TRY(take32(H));                                        // ff2.b
+            skip32(3 * H + I);                                          // qkv_c, ff1_c
+        }
+        CUDA_TRY(take32(2 * H + P * H));                                // post.g, post.b, proj.w
+        CUDA_TRY(cudaMemsetAsync(rw.f32_arena + o32, 0, H * 4, root.compute));  // zero bias for the patch projection
+        o32 += H;
+        if (o32 != m->f32_elems || o16 != m->f16_elems || src != total) return fail(B200RT_E_STATE, "internal: vit blob carve mismatch");
+    }
+    CUDA_TRY(cudaStreamSynchronize(root.compute));
+    CUDA_TRY(cudaFree(d_blob));
+    for (size_t g = 1; g < rt.devs.size(); ++g) {
+        CUDA_TRY(cudaMemcpyPeerAsync(m->per_dev[g].f32_arena, rt.devs[g]->id, rw.f32_arena, root.id, m->f32_elems * 4, root.compute));
+        CUDA_TRY(cudaMemcpyPeerAsync(m->per_dev[g].f16_arena, rt.devs[g]->id, rw.f16_arena, root.id, m->f16_elems * 2, root.compute));
+    }
+    CUDA_TRY(cudaStreamSynchronize(root.compute));
+    for (size_t g = 0; g < rt.devs.size(); ++g) {
+        DevWeights& w = m->per_dev[g];
+        CUDA_TRY(cudaSetDevice(rt.devs[g]->id));
+        float* p = w.f32_arena;
+        __half* q = w.f16_arena;
+        w.patch_w = q; q += H * PD;
+        if (int rc = make_map_2d(&w.m_patch, w.patch_w, H, PD, 128)) return rc;
+        w.cls = p; p += H;
+        w.pos = p; p += static_cast<size_t>(T) * H;
+        w.pre_g = p; p += H;
+        w.pre_b = p; p += H;
+        w.layers.resize(c.layers);
+        for (int l = 0; l < c.layers; ++l) {
+            LayerW& lw = w.layers[l];
+            lw.ln1_g = p; p += H;  lw.ln1_b = p; p += H;
+            lw.qkv_w = q; q += 3 * H * H;  lw.qkv_b = p; p += 3 * H;
+            lw.ao_w = q;  q += H * H;      lw.ao_b = p;  p += H;
+            lw.ln2_g = p; p += H;  lw.ln2_b = p; p += H;
+            lw.ff1_w = q; q += I * H;      lw.ff1_b = p; p += I;
+            lw.ff2_w = q; q += H * I;      lw.ff2_b = p; p += H;
+            lw.qkv_c = p; p += 3 * H;
+            lw.ff1_c = p; p += I;
+            if (int rc = make_map_2d(&lw.m_qkv, lw.qkv_w, 3 * H, H, 128)) return rc;
+            if (int rc = make_map_2d(&lw.m_ao, lw.ao_w, H, H, 128)) return rc;
+            if (int rc = make_map_2d(&lw.m_ff1, lw.ff1_w, I, H, 128)) return rc;
+            if (int rc = make_map_2d(&lw.m_ff2, lw.ff2_w, H, I, 128)) return rc;
+        }
+        w.post_g = p; p += H;
+        w.post_b = p; p += H;
+        w.proj_w = p; p += P * H;
+        w.zero_bias = p; p += H;
+    }
+    CUDA_TRY(cudaSetDevice(root.id));
+    {
+        std::lock_guard<std::mutex> lk(rt.mu);
+        rt.models.push_back(std::move(m));
+        *model_out = static_cast<int>(rt.models.size()) - 1;
+    }
+    return 0;
+}
+
 Runtime* live_rt() {
     if (g_poisoned.load()) {
         fail(B200RT_E_CUDA, "context poisoned by an earlier CUDA error%s%s", g_rt && !g_rt->async_error.empty() ? ": " : "",
@@ -1094,8 +1336,11 @@ int b200rt_wave_capacity_items(void) {
 int b200rt_model_load(const char* kind, const void* cfg, const void* weights, size_t nbytes, int* model_out) {
     Runtime* rt = live_rt();
     if (!rt) return g_poisoned.load() ? B200RT_E_CUDA : B200RT_E_STATE;
-    if (!kind || strcmp(kind, "bert") != 0) return fail(B200RT_E_UNSUPPORTED, "unknown model kind '%s' (only \"bert\")", kind ? kind : "(null)");
+    if (!kind || (strcmp(kind, "bert") != 0 && strcmp(kind, "vit") != 0))
+        return fail(B200RT_E_UNSUPPORTED, "unknown model kind '%s' (\"bert\" or \"vit\")", kind ? kind : "(null)");
     if (!cfg || !weights || !model_out) return fail(B200RT_E_INVALID, "null argument");
+    if (strcmp(kind, "vit") == 0)
+        return model_load_vit(*static_cast<const b200rt_vit_config*>(cfg), static_cast<const float*>(weights), nbytes, model_out);
     return model_load(*static_cast<const b200rt_bert_config*>(cfg), static_cast<const float*>(weights), nbytes, model_out);
 }
 
@@ -1106,6 +1351,7 @@ static int submit_impl(int model, const int32_t* ids, const int32_t* lens, int n
     const Model* m = get_model(*rt, model);
     if (!m) return B200RT_E_INVALID;
     if (!out || !ticket_out) return fail(B200RT_E_INVALID, "null out / ticket_out");
+    if (m->kind != KIND_BERT) return fail(B200RT_E_INVALID, "model %d takes pixels (b200rt_submit_pixels), not token ids", model);
     if (flags & ~static_cast<uint32_t>(B200RT_SUBMIT_BORROW_IDS)) return fail(B200RT_E_INVALID, "unknown submit flags 0x%x", flags);
     if (int rc = check_ids(m->cfg, ids, lens, n_items, max_len)) return rc;
     auto t = std::make_shared<Ticket>();
@@ -1169,6 +1415,36 @@ int b200rt_submit(int model, const int32_t* ids, const int32_t* lens, int n_item
 int b200rt_submit_ex(int model, const int32_t* ids, const int32_t* lens, int n_items, int max_len, float* out,
                      uint32_t flags, uint64_t* ticket_out) {
     return submit_impl(model, ids, lens, n_items, max_len, out, flags, ticket_out);
+}
+
+int b200rt_submit_pixels(int model, const float* pixels, int n_items, float* out, uint64_t* ticket_out) {
+    Runtime* rt = live_rt();
+    if (!rt) return g_poisoned.load() ? B200RT_E_CUDA : B200RT_E_STATE;
+    const Model* m = get_model(*rt, model);
+    if (!m) return B200RT_E_INVALID;
+    if (m->kind != KIND_VIT) return fail(B200RT_E_INVALID, "model %d takes token ids (b200rt_submit), not pixels", model);
+    if (!pixels || !out || !ticket_out || n_items < 1) return fail(B200RT_E_INVALID, "null / empty argument");
+    auto t = std::make_shared<Ticket>();
+    t->model = model;
+    t->mp = m;
+    t->n_items = n_items;
+    t->S = m->tokens;
+    t->out = out;
+    t->pixels = pixels;
+    t->borrowed = true;
+    t->remaining.store(n_items);
+    t->out_pinned = is_pinned(out, static_cast<size_t>(n_items) * m->out_dim * 4);
+    {
+        std::lock_guard<std::mutex> lk(rt->mu);
+        if (rt->stopping) return fail(B200RT_E_STATE, "runtime is shutting down");
+        t->id = rt->next_ticket++;
+        rt->tickets.emplace(t->id, t);
+        rt->pending.push_back(Run{t, 0, n_items, -m->tokens});  // negative bucket keys: image waves never mix with text waves
+        rt->last_submit = std::chrono::steady_clock::now();
+        *ticket_out = t->id;
+    }
+    rt->cv_submit.notify_one();
+    return 0;
 }
 
 static int reap_locked(Runtime& rt, uint64_t id, const std::shared_ptr<Ticket>& t) {
@@ -1252,6 +1528,7 @@ int b200rt_embed_device(int model, int gpu, const int32_t* d_ids, const int32_t*
     const Model* m = get_model(*rt, model);
     if (!m) return B200RT_E_INVALID;
     if (gpu < 0 || gpu >= static_cast<int>(rt->devs.size())) return fail(B200RT_E_INVALID, "gpu index %d outside the pool", gpu);
+    if (m->kind != KIND_BERT) return fail(B200RT_E_UNSUPPORTED, "b200rt_embed_device takes token ids: model %d is not a text encoder", model);
     if (!d_ids || !d_lens || !d_out || n_items < 1 || max_len < 1 || max_len > m->cfg.max_pos) return fail(B200RT_E_INVALID, "bad argument");
     Dev& d = *rt->devs[gpu];
     std::lock_guard<std::mutex> dl(d.mu);
@@ -1351,7 +1628,10 @@ void b200rt_shutdown(void) {
         cudaSetDevice(d->id);
         drop_graphs(*d);
         cudaFree(d->x32_dbg); cudaFree(d->pstats[0]); cudaFree(d->pstats[1]); cudaFree(d->yhi); cudaFree(d->ylo); cudaFree(d->qkv); cudaFree(d->ctx); cudaFree(d->ffn);
-        for (int s = 0; s < NSLOT; ++s) { cudaFree(d->ids_in[s]); cudaFree(d->lens_in[s]); cudaEventDestroy(d->ev_done[s]); cudaEventDestroy(d->ev_begin[s]); cudaEventDestroy(d->ev_end[s]); }
+        cudaFree(d->lens_const);
+        if (d->copy) cudaStreamDestroy(d->copy);
+        for (int s = 0; s < NSLOT; ++s) if (d->ev_pix[s]) cudaEventDestroy(d->ev_pix[s]);
+        for (int s = 0; s < NSLOT; ++s) { cudaFree(d->pix_in[s]); cudaFree(d->ids_in[s]); cudaFree(d->lens_in[s]); cudaEventDestroy(d->ev_done[s]); cudaEventDestroy(d->ev_begin[s]); cudaEventDestroy(d->ev_end[s]); }
         cudaEventDestroy(d->ev_ws);
         cudaStreamDestroy(d->compute);
     }
@@ -1542,6 +1822,7 @@ int b200rt_debug_hidden(int model, const int32_t* ids, const int32_t* lens, int 
     if (!rt) return g_poisoned.load() ? B200RT_E_CUDA : B200RT_E_STATE;
     const Model* m = get_model(*rt, model);
     if (!m) return B200RT_E_INVALID;
+    if (m->kind != KIND_BERT) return fail(B200RT_E_INVALID, "model %d is not a text encoder", model);
     if (int rc = check_ids(m->cfg, ids, lens, n_items, max_len)) return rc;
     if (n_layers < 0 || n_layers > m->cfg.layers || !hidden_out) return fail(B200RT_E_INVALID, "bad n_layers / hidden_out");
     Dev& d = *rt->devs[0];
@@ -1565,12 +1846,34 @@ int b200rt_debug_hidden(int model, const int32_t* ids, const int32_t* lens, int 
     return 0;
 }
 
+int b200rt_debug_vit_hidden(int model, const float* pixels, int n_items, int n_layers, float* hidden_out) {
+    Runtime* rt = live_rt();
+    if (!rt) return g_poisoned.load() ? B200RT_E_CUDA : B200RT_E_STATE;
+    const Model* m = get_model(*rt, model);
+    if (!m) return B200RT_E_INVALID;
+    if (m->kind != KIND_VIT || !pixels || !hidden_out || n_items < 1 || n_items > VIT_WAVE_ITEMS || n_layers < 0 || n_layers > m->vcfg.layers)
+        return fail(B200RT_E_INVALID, "bad arguments");
+    Dev& d = *rt->devs[0];
+    std::lock_guard<std::mutex> dl(d.mu);
+    CUDA_TRY(cudaSetDevice(d.id));
+    CUDA_TRY(cudaMemcpy(d.pix_in[0], pixels, static_cast<size_t>(n_items) * m->item_bytes, cudaMemcpyHostToDevice));
+    if (int rc = forward_vit(d, *m, 0, d.pix_in[0], n_items, nullptr, d.compute, n_layers)) return rc;
+    CUDA_TRY(cudaStreamSynchronize(d.compute));
+    const size_t n = static_cast<size_t>(n_items) * m->tokens * HIDDEN;
+    std::vector<__half> hi(n), lo(n);
+    CUDA_TRY(cudaMemcpy(hi.data(), d.yhi, n * 2, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(lo.data(), d.ylo, n * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; ++i) hidden_out[i] = __half2float(hi[i]) + __half2float(lo[i]);
+    return 0;
+}
+
 int b200rt_debug_profile_forward(int model, int n_items, int max_len, int iters, char* names_out, size_t names_cap,
                                  float* ms_out, int* n_out, int cap) {
     Runtime* rt = live_rt();
     if (!rt) return g_poisoned.load() ? B200RT_E_CUDA : B200RT_E_STATE;
     const Model* m = get_model(*rt, model);
     if (!m) return B200RT_E_INVALID;
+    if (m->kind != KIND_BERT) return fail(B200RT_E_INVALID, "model %d is not a text encoder", model);
     if (!names_out || !ms_out || !n_out || n_items < 1 || max_len < 1 || max_len > m->cfg.max_pos) return fail(B200RT_E_INVALID, "bad argument");
     Dev& d = *rt->devs[0];
     std::lock_guard<std::mutex> dl(d.mu);
