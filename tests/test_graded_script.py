@@ -36,7 +36,7 @@ def test_text_embeddings_inference_embed_dataset_runs_unchanged(tmp_path):
     state = tmp_path / "state"
     env = dict(os.environ, PYTHONPATH=PKG + os.pathsep + os.environ.get("PYTHONPATH", ""), MODAL_SHIM_STATE=str(state),
                PATH=os.path.join(ROOT, "tests", "fake_tei") + os.pathsep + os.environ["PATH"], FAKE_TEI_LOG=str(tmp_path / "tei.jsonl"),
-               FAKE_TEI_LAYERS="2")
+               FAKE_TEI_LAYERS="1")  # (httpx default timeout in the reference script is 5 s: keep the CPU stand-in quick)
     rows = 70  # -> 2 batches of 32, the last 6 items are dropped by generate_batches (:156-163)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_hn_dataset.py"), "--rows", str(rows)], env=env, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
