@@ -55,6 +55,9 @@ typedef struct b200rt_stats_t {
  * access between all of them and starts the scheduler threads.  devices = NULL means 0..n_gpus-1.    */
 /* flags: bits 0-15 = items of 512 tokens one replica takes per wave (0 = default 128), see B200RT_INIT_WAVE_ITEMS */
 #define B200RT_INIT_WAVE_ITEMS(n) ((uint32_t)(n) & 0xFFFFu)
+/*        bits 16-23 = k > 0: TWO replicas per GPU; each replica's GEMM launches ask for (SMs - k) SMs and its attention launches
+ *        for k, so that one replica's attention (MUFU-bound, light on L2) runs beside the other's GEMMs (L2-fill-bound).       */
+#define B200RT_INIT_SPLIT_SMS(k) (((uint32_t)(k) & 0xFFu) << 16)
 int b200rt_init(int n_gpus, uint32_t flags);
 int b200rt_init_devices(const int* devices, int n_gpus, uint32_t flags);
 int b200rt_num_gpus(void);

@@ -595,16 +595,32 @@ cudaError_t attention_init_device() {
 }
 
 cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tctx, const int32_t* lens, int B, int S, int sm_count,
-                             cudaStream_t stream, unsigned long long* dbg) {
+                             cudaStream_t stream, unsigned long long* dbg, bool pairs) {
     if (S < 1 || S > attn::MAX_KB * attn::KB || B < 1 || sm_count < 1) return cudaErrorInvalidValue;
     // fewer (item, head) units than SMs: split them by query tile (K and V are then loaded once per tile, but a single item
     // spreads over 48 SMs instead of 12)
     const int nq = (S + attn::QT - 1) / attn::QT;
     const int split = (B * HEADS < sm_count && nq > 1) ? 1 : 0;
     const int n_units = B * HEADS * (split ? nq : 1);
-    const int grid = n_units < sm_count ? n_units : sm_count;
-    attn::attention_kernel<<<grid, attn::NUM_THREADS, attn::SMEM_BYTES, stream>>>(tq, tctx, lens, S, split, n_units, dbg);
-    return cudaGetLastError();
+    int grid = n_units < sm_count ? n_units : sm_count;
+    if (!pairs || grid < 2) {
+        attn::attention_kernel<<<grid, attn::NUM_THREADS, attn::SMEM_BYTES, stream>>>(tq, tctx, lens, S, split, n_units, dbg);
+        return cudaGetLastError();
+    }
+    grid &= ~1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(attn::NUM_THREADS);
+    cfg.dynamicSmemBytes = attn::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, attn::attention_kernel, tq, tctx, lens, S, split, n_units, dbg);
 }
 
 }  // namespace b200

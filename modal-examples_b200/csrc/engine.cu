@@ -172,6 +172,8 @@ struct Model {
 struct Dev {
     int id = -1;
     int sm_count = 148;
+    int sm_gemm = 148, sm_attn = 148;  // SMs a GEMM / an attention launch of this replica asks for (see B200RT_INIT_SPLIT_SMS)
+    bool attn_pairs = false;           // launch the attention CTAs as clusters of 2 so that they take whole TPCs
     cudaStream_t compute = nullptr;
     // workspace (capacity cap_rows rows)
     __half *yhi = nullptr, *ylo = nullptr;  // residual stream y = hi + lo, PRE-LayerNorm; hi doubles as the GEMM A operand
@@ -342,20 +344,20 @@ int forward_enqueue(Dev& d, const Model& m, int dev_index, const int32_t* ids, c
         const LayerW& lw = w.layers[l];
         // QKV = LN_prev(y) Wqkv^T + b, the LayerNorm folded into the epilogue
         GemmEpi e_qkv{lw.qkv_c, d.pstats[0], STAT_PARTS, nullptr, nullptr, nullptr, c.eps};
-        CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_yhi, lw.m_qkv, d.m_qkv2d, nullptr, e_qkv, M, QKV_DIM, HIDDEN, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_yhi, lw.m_qkv, d.m_qkv2d, nullptr, e_qkv, M, QKV_DIM, HIDDEN, d.sm_gemm, stream));
         ++nl; mark("gemm_qkv");
-        CUDA_TRY(launch_attention(*mq, *mc, lens, B, S, d.sm_count, stream));
+        CUDA_TRY(launch_attention(*mq, *mc, lens, B, S, d.sm_attn, stream, nullptr, d.attn_pairs));
         ++nl; mark("attention");
         // y <- ctx Wao^T + b + LN_prev(y); new row statistics (LN1's) into pstats[1]
         GemmEpi e_ao{lw.ao_b, d.pstats[0], STAT_PARTS, prev_g, prev_b, d.pstats[1], c.eps};
-        CUDA_TRY(launch_gemm(EPI_BIAS_RES_SPLIT, d.m_ctx, lw.m_ao, d.m_yhi_c, &d.m_ylo_c, e_ao, M, HIDDEN, HIDDEN, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_SPLIT, d.m_ctx, lw.m_ao, d.m_yhi_c, &d.m_ylo_c, e_ao, M, HIDDEN, HIDDEN, d.sm_gemm, stream));
         ++nl; mark("gemm_attn_out");
         GemmEpi e_ff1{lw.ff1_c, d.pstats[1], STAT_PARTS, nullptr, nullptr, nullptr, c.eps};
-        CUDA_TRY(launch_gemm(EPI_BIAS_GELU_F16, d.m_yhi, lw.m_ff1, d.m_ffn, nullptr, e_ff1, M, c.inter, HIDDEN, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_GELU_F16, d.m_yhi, lw.m_ff1, d.m_ffn, nullptr, e_ff1, M, c.inter, HIDDEN, d.sm_gemm, stream));
         ++nl; mark("gemm_ffn1_gelu");
         // y <- ffn W2^T + b + LN1(y); LN2's statistics into pstats[0]
         GemmEpi e_ff2{lw.ff2_b, d.pstats[1], STAT_PARTS, lw.ln1_g, lw.ln1_b, d.pstats[0], c.eps};
-        CUDA_TRY(launch_gemm(EPI_BIAS_RES_SPLIT, d.m_ffn, lw.m_ff2, d.m_yhi_c, &d.m_ylo_c, e_ff2, M, HIDDEN, c.inter, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_SPLIT, d.m_ffn, lw.m_ff2, d.m_yhi_c, &d.m_ylo_c, e_ff2, M, HIDDEN, c.inter, d.sm_gemm, stream));
         ++nl; mark("gemm_ffn2");
         prev_g = lw.ln2_g;
         prev_b = lw.ln2_b;
@@ -389,20 +391,20 @@ int forward_enqueue_vit(Dev& d, const Model& m, int dev_index, const float* pixe
     // embeddings, pre_layrnorm -> residual stream + statistics
     CUDA_TRY(launch_im2col(pixels, d.ffn, B, c.image, c.patch, stream));
     GemmEpi e_patch{w.zero_bias, nullptr, STAT_PARTS, nullptr, nullptr, nullptr, c.eps};
-    CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_im2col, w.m_patch, d.m_ctx, nullptr, e_patch, M, HIDDEN, 3 * c.patch * c.patch, d.sm_count, stream));
+    CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_im2col, w.m_patch, d.m_ctx, nullptr, e_patch, M, HIDDEN, 3 * c.patch * c.patch, d.sm_gemm, stream));
     CUDA_TRY(launch_vit_embed(d.ctx, w.cls, w.pos, w.pre_g, w.pre_b, d.yhi, d.ylo, d.pstats[0], M, T, c.eps, stream));
     nl += 3;
     for (int l = 0; l < L; ++l) {
         const LayerW& lw = w.layers[l];
         GemmEpi e_qkv{lw.qkv_c, d.pstats[0], STAT_PARTS, nullptr, nullptr, nullptr, c.eps};
-        CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_yhi, lw.m_qkv, d.m_qkv2d, nullptr, e_qkv, M, QKV_DIM, HIDDEN, d.sm_count, stream));
-        CUDA_TRY(launch_attention(*mq, *mc, d.lens_const, B, T, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_F16, d.m_yhi, lw.m_qkv, d.m_qkv2d, nullptr, e_qkv, M, QKV_DIM, HIDDEN, d.sm_gemm, stream));
+        CUDA_TRY(launch_attention(*mq, *mc, d.lens_const, B, T, d.sm_attn, stream, nullptr, d.attn_pairs));
         GemmEpi e_ao{lw.ao_b, nullptr, STAT_PARTS, nullptr, nullptr, d.pstats[1], c.eps};  // h += ctx Wo^T + b (raw residual)
-        CUDA_TRY(launch_gemm(EPI_BIAS_RES_SPLIT, d.m_ctx, lw.m_ao, d.m_yhi_c, &d.m_ylo_c, e_ao, M, HIDDEN, HIDDEN, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_SPLIT, d.m_ctx, lw.m_ao, d.m_yhi_c, &d.m_ylo_c, e_ao, M, HIDDEN, HIDDEN, d.sm_gemm, stream));
         GemmEpi e_ff1{lw.ff1_c, d.pstats[1], STAT_PARTS, nullptr, nullptr, nullptr, c.eps};
-        CUDA_TRY(launch_gemm(EPI_BIAS_QGELU_F16, d.m_yhi, lw.m_ff1, d.m_ffn, nullptr, e_ff1, M, c.inter, HIDDEN, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_QGELU_F16, d.m_yhi, lw.m_ff1, d.m_ffn, nullptr, e_ff1, M, c.inter, HIDDEN, d.sm_gemm, stream));
         GemmEpi e_ff2{lw.ff2_b, nullptr, STAT_PARTS, nullptr, nullptr, d.pstats[0], c.eps};
-        CUDA_TRY(launch_gemm(EPI_BIAS_RES_SPLIT, d.m_ffn, lw.m_ff2, d.m_yhi_c, &d.m_ylo_c, e_ff2, M, HIDDEN, c.inter, d.sm_count, stream));
+        CUDA_TRY(launch_gemm(EPI_BIAS_RES_SPLIT, d.m_ffn, lw.m_ff2, d.m_yhi_c, &d.m_ylo_c, e_ff2, M, HIDDEN, c.inter, d.sm_gemm, stream));
         nl += 5;
     }
     if (n_layers < 0) {
@@ -915,6 +917,14 @@ int alloc_dev(Runtime& rt, Dev& d) {
     if (prop.major != 10)
         return fail(B200RT_E_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", d.id, prop.major, prop.minor);
     d.sm_count = prop.multiProcessorCount;
+    if (d.sm_attn >= d.sm_count || d.sm_attn < 2) {  // whole-GPU replica
+        d.sm_gemm = d.sm_attn = d.sm_count;
+        d.attn_pairs = false;
+    } else {  // two replicas share this GPU: GEMM launches leave sm_attn SMs to the other replica's attention launches
+        d.sm_attn &= ~1;
+        d.sm_gemm = (d.sm_count - d.sm_attn) & ~1;
+        d.attn_pairs = true;
+    }
     CUDA_TRY(kernels_init_device());
     CUDA_TRY(cudaStreamCreateWithFlags(&d.compute, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&d.ev_ws, cudaEventDisableTiming));
@@ -955,7 +965,7 @@ int rt_init(const int* devices, int n, uint32_t flags) {
     std::lock_guard<std::mutex> lk(g_rt_mu);
     if (g_rt) return fail(B200RT_E_STATE, "b200rt already initialised");
     if (g_poisoned.load()) return fail(B200RT_E_CUDA, "context poisoned by an earlier CUDA error");
-    if (n < 1 || n > ScatterPlan::MAX_SHARDS) return fail(B200RT_E_INVALID, "n_gpus must be in [1, 8], got %d", n);
+    if (n < 1 || n > ScatterPlan::MAX_SHARDS) return fail(B200RT_E_INVALID, "n_gpus must be in [1, %d], got %d", ScatterPlan::MAX_SHARDS, n);
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0)
@@ -967,17 +977,23 @@ int rt_init(const int* devices, int n, uint32_t flags) {
     g_rt = rt.get();  // forward() and friends read capacity through g_rt
     auto bail = [&](int rc) { g_rt = nullptr; return rc; };
     if (int rc = load_driver_entry()) return bail(rc);
+    const int split_sms = static_cast<int>((flags >> 16) & 0xFFu);  // B200RT_INIT_SPLIT_SMS(k): two replicas per GPU
+    if (split_sms && 2 * n > ScatterPlan::MAX_SHARDS) return bail(fail(B200RT_E_INVALID, "split replicas: at most %d GPUs", ScatterPlan::MAX_SHARDS / 2));
     for (int i = 0; i < n; ++i) {
-        auto d = std::make_unique<Dev>();
-        d->id = devices ? devices[i] : i;
-        if (d->id < 0 || d->id >= count) return bail(fail(B200RT_E_INVALID, "device %d not present (%d visible)", d->id, count));
-        if (int rc = alloc_dev(*rt, *d)) return bail(rc);
-        rt->devs.push_back(std::move(d));
+        for (int half = 0; half < (split_sms ? 2 : 1); ++half) {
+            auto d = std::make_unique<Dev>();
+            d->id = devices ? devices[i] : i;
+            if (d->id < 0 || d->id >= count) return bail(fail(B200RT_E_INVALID, "device %d not present (%d visible)", d->id, count));
+            d->sm_attn = split_sms ? split_sms : 1 << 20;
+            if (int rc = alloc_dev(*rt, *d)) return bail(rc);
+            rt->devs.push_back(std::move(d));
+        }
     }
+    n = static_cast<int>(rt->devs.size());
     // peer access both ways between every pair (scatter writes root->peer, gather writes peer->root)
     for (int i = 0; i < n; ++i)
         for (int j = 0; j < n; ++j) {
-            if (i == j) continue;
+            if (i == j || rt->devs[i]->id == rt->devs[j]->id) continue;
             int can = 0;
             cudaDeviceCanAccessPeer(&can, rt->devs[i]->id, rt->devs[j]->id);
             if (!can) return bail(fail(B200RT_E_UNSUPPORTED, "no peer access between GPU %d and %d", rt->devs[i]->id, rt->devs[j]->id));

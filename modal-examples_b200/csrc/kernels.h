@@ -60,8 +60,9 @@ cudaError_t launch_fold_ln(const float* w, const float* gamma, const float* beta
 // lens[B] valid keys per item, ctx fp16 [B*S, 768].  tq: 3D map over qkv {2304, S, B}, tctx: 3D map over ctx {768, S, B};
 // both box {64,128,1}, 128B swizzle.  Persistent: min(units, sm_count) CTAs walk the (item, head[, query tile]) units.
 // dbg: B200RT_DIAG builds only -- device buffer of 5*32*8 clock stamps written by CTA 0 (NULL in the product path)
+// pairs: launch the CTAs as clusters of 2 (no cooperation: only so that they occupy whole TPCs next to a CTA-pair GEMM)
 cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tctx, const int32_t* lens, int B, int S, int sm_count,
-                             cudaStream_t stream, unsigned long long* dbg = nullptr);
+                             cudaStream_t stream, unsigned long long* dbg = nullptr, bool pairs = false);
 
 // word + position + token_type(0) embedding gather -> y = hi + lo (pre-LN residual stream) + the row's statistic partials.
 cudaError_t launch_embed(const int32_t* ids, const float* word, const float* pos, const float* type0, __half* yhi, __half* ylo,
@@ -90,7 +91,7 @@ cudaError_t launch_f32_to_f16(const float* src, __half* dst, size_t n, cudaStrea
 
 // Root-side scatter of a wave's token ids / lengths into each shard's (possibly peer) input slot.
 struct ScatterPlan {
-    static constexpr int MAX_SHARDS = 8;
+    static constexpr int MAX_SHARDS = 16;
     int n_shards;
     int S;  // padded length of every item in the wave
     int32_t* dst_ids[MAX_SHARDS];

@@ -17,6 +17,14 @@ import threading
 import time
 import uuid
 
+# The map pump is many threads that each hold the GIL for microseconds between long GIL-free waits inside libb200rt.  With
+# CPython's default 5 ms switch interval a worker returning from the C ABI can sit behind another thread's Python work for
+# milliseconds -- longer than a wave takes on 8 GPUs.  The in-box runtime owns the process, so it shortens the interval.
+import sys as _sys
+
+if _sys.getswitchinterval() > 5e-4:
+    _sys.setswitchinterval(5e-4)
+
 _in_worker = contextvars.ContextVar("modal_shim_in_worker", default=False)
 _task_ids = itertools.count(1)
 
