@@ -291,3 +291,16 @@ def test_error_behaviour(rt):
     with pytest.raises(rt.B200RTError):
         rt.EmbedModel(dict(R.geometry_dict(g), hidden=1024), R.pack_blob(flat, g))  # unsupported geometry
     assert model.embed(np.full((1, 1), 101, np.int32)).shape == (1, 768)  # minimum size still works
+
+
+def test_attention_randomised_stress():
+    """tools/attn_stress.py in its own process: random (B, S, lens, score scale) draws -- several units per persistent CTA,
+    split and unsplit launches, 1..8 sub-blocks, forced accumulator rescales -- each run twice for bitwise determinism."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, STRESS_CASES="16", STRESS_SEED="7")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "attn_stress.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "failures: 0" in r.stdout
