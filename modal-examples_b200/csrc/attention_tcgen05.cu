@@ -246,6 +246,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             // short units would start on the second phase of somebody else's slot.  scnt packs, per warpgroup, its S count
             // modulo 4 (bits 4w, 4w+1) and whether it is >= 2 (bit 4w+2).
             uint32_t scnt = 0;
+#ifdef B200RT_DIAG
+            int sdbg = 0;
+#endif
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const Unit U = decode_unit(u, nq_all, split, lens, S);
                 int t = 0, sb = 0;
@@ -255,16 +258,23 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                     const uint32_t slot = 2 * wg + (cw & 1);
                     const uint32_t g = gt + t;
                     ATT_PROG(1, u, c, slot);
+                    ATT_STAMP(5, sdbg, 0);
                     if (sb == 0) mbar_wait(&q_full[g & 1], (g >> 1) & 1);
                     if (t == 0 && (sb & 1) == 0) mbar_wait(&k_full[sb >> 1], (k_par >> (sb >> 1)) & 1);  // first touch of the K tile
+                    ATT_STAMP(5, sdbg, 1);
                     if (cw & 4) mbar_wait(&s_free[slot], (((cw >> 1) & 1) ^ 1));                          // the slot's previous S
                     tc_fence_after();
+                    ATT_STAMP(5, sdbg, 2);
 #pragma unroll
                     for (int k = 0; k < D / 16; ++k) {
                         umma_f16_ss(tmem_base + TM_S + slot * SB, make_sw128_desc(q_addr + (g & 1) * TILE_BYTES + k * 32),
                                     make_sw128_desc(k_addr + sb * (SB * 128) + k * 32), idesc_s, k != 0);
                     }
                     umma_commit(&s_full[slot]);
+                    ATT_STAMP(5, sdbg, 3);
+#ifdef B200RT_DIAG
+                    ++sdbg;
+#endif
                     // the unit's last tile is through with K tile j after its odd sub-block (or the last one): free it
                     if (t == U.nq - 1 && ((sb & 1) == 1 || sb == U.nsb - 1)) umma_commit(&k_free[sb >> 1]);
                     {   // count: (low two bits + 1) mod 4, sticky ">= 2"
@@ -296,7 +306,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 uint32_t pb = U.c_off;
                 for (int c = 0; c < U.total; ++c) {
                     ATT_PROG(2, u, c, g);
+                    ATT_STAMP(6, g, 0);
                     mbar_wait(&pv_done[pb], (phases >> pb) & 1);
+                    ATT_STAMP(6, g, 1);
                     phases ^= 1u << pb;
                     ++g;
                     asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(retired)), "r"(g) : "memory");
@@ -325,6 +337,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                     ATT_STAMP(4, gs_dbg, 0);
                     ATT_PROG(3, u, c, pb);
                     mbar_wait(&p_full[pb], (phases >> pb) & 1);
+                    ATT_STAMP(4, gs_dbg, 3);
                     phases ^= 1u << pb;
                     if (sb == 0 && g >= 2) mbar_wait(&o_free[g & 1], ((g >> 1) - 1) & 1);  // tile g-2 has been written out
                     if (t == 0 && (sb & 1) == 0) mbar_wait(&v_full[sb >> 1], (v_par >> (sb >> 1)) & 1);
@@ -349,6 +362,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                         ++t;
                     }
                     if (++pb == NEXP) pb = 0;
+                    ATT_STAMP(4, gs_dbg - 1, 4);
                 }
                 v_par ^= (1u << U.nkb) - 1;
                 gt += U.nq;
@@ -367,8 +381,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
         const uint32_t mr_self = mr_base + w * QT * 4;
         const uint32_t ls_self = smem_u32(smem + OFF_LS) + (w * QT + r) * 8;
         const uint32_t swz = static_cast<uint32_t>(r & 7);
-        const bool obs = (warp & 3) == 0 && lane == 0;
-        (void)obs;
+        const bool obs = lane == 0 && ((warp & 3) == 0 || w == 0);
+        const int ow = (warp & 3) == 0 ? w : 6 + (warp & 3);  // observer row: warp 0 of every warpgroup, all warps of warpgroup 0
+        (void)obs; (void)ow;
         uint32_t need_own = 0;                // 1 + the running index of this warpgroup's previous sub-block (0: none yet)
         uint32_t scnt = 0;                    // sub-blocks this warpgroup has taken so far
         const uint32_t retired_addr = smem_u32(retired);
@@ -398,12 +413,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 const uint32_t g = gs_base + c;
                 const uint32_t slot = 2 * w + (scnt & 1);  // this warpgroup's own two S slots, alternately (see the S issuer)
                 const uint32_t gtile = gt + t;
-                if (obs) ATT_STAMP(w, g, 0);
+                if (obs) ATT_STAMP(ow, g, 0);
                 if (obs) ATT_PROG(4 + w, u, c, 1);
                 mbar_wait(&s_full[slot], (scnt >> 1) & 1);
                 ++scnt;
                 tc_fence_after();
-                if (obs) ATT_STAMP(w, g, 1);
+                if (obs) ATT_STAMP(ow, g, 1);
                 const int valid = U.len - sb * SB;  // keys [0, valid) of this sub-block are real (>= 1)
                 uint32_t v[64];
                 auto load_scores = [&]() {
@@ -427,7 +442,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 float m_used = mx, m_prev = mx;
                 const int pred_wg = c > 0 ? wp : prev_last_wg;
                 if (obs) ATT_PROG(4 + w, u, c, 2 + 16 * (pred_wg + 1));
+                if (obs) ATT_STAMP(ow, g, 5);
                 if (pred_wg >= 0 && pred_wg != w) named_bar_sync(BAR_MAX + pred_wg * NEXP + w, 256);  // the predecessor's max is in smem
+                if (obs) ATT_STAMP(ow, g, 6);
                 if (sb != 0) {
                     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(m_prev) : "r"(mr_base + wp * QT * 4) : "memory");
                     m_used = (mx - m_prev > kRescaleThreshold) ? mx : m_prev;
@@ -442,7 +459,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                     l_w *= ex2_approx((m_ref - m_used) * kScaleLog2e);
                 }
                 m_ref = m_used;
-                if (obs) ATT_STAMP(w, g, 2);
+                if (obs) ATT_STAMP(ow, g, 2);
                 if (sb != 0 && __any_sync(0xffffffffu, m_used != m_prev)) {
                     // rare: rescale this warp's 32 rows of the accumulator by 2^((m_prev - m_used) k) (1 where unchanged).
                     // The scores are dropped and read again afterwards so that this path costs the common one no registers.
@@ -470,7 +487,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 wait_retired(need_own);  // the previous P of this buffer has been consumed
                 if (obs) ATT_PROG(4 + w, u, c, 5);
                 need_own = g + 1;
-                if (obs) ATT_STAMP(w, g, 3);
+                if (obs) ATT_STAMP(ow, g, 3);
                 float ls0 = 0.f, ls1 = 0.f;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -495,7 +512,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 fence_proxy_async_smem();  // P_c visible to the tensor core's async-proxy reads
                 mbar_arrive(&p_full[w]);   // (release: also publishes (m, l) to the epilogue via the o_done chain)
                 if (obs) ATT_PROG(4 + w, u, c, 6);
-                if (obs) ATT_STAMP(w, g, 4);
+                if (obs) ATT_STAMP(ow, g, 4);
                 sb += NEXP;
                 while (sb >= U.nsb && t < U.nq) {
                     sb -= U.nsb;

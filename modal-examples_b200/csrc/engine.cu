@@ -1800,7 +1800,7 @@ int b200rt_debug_attention(const uint16_t* qkv, const int32_t* lens, uint16_t* c
 #ifdef B200RT_DIAG
     if (const char* path = getenv("B200RT_ATTN_STAMPS")) {  // diagnostics: per-phase clock stamps of CTA 0 -> text file
         unsigned long long* dstamp = nullptr;
-        std::vector<unsigned long long> hs(5 * 32 * 8, 0);
+        std::vector<unsigned long long> hs(10 * 32 * 8, 0);
         CUDA_TRY(cudaMalloc(&dstamp, hs.size() * 8));
         CUDA_TRY(cudaMemset(dstamp, 0, hs.size() * 8));
         CUDA_TRY(launch_attention(tq, tc, dl_, B, S, d.sm_count, d.compute, dstamp));
@@ -1809,8 +1809,8 @@ int b200rt_debug_attention(const uint16_t* qkv, const int32_t* lens, uint16_t* c
         unsigned long long t0 = ~0ull;
         for (auto v : hs) if (v && v < t0) t0 = v;
         if (FILE* f = fopen(path, "w")) {
-            const char* names[5] = {"exp_wg0", "exp_wg1", "exp_wg2", "epilogue", "pv"};
-            for (int o = 0; o < 5; ++o)
+            const char* names[10] = {"exp_wg0", "exp_wg1", "exp_wg2", "epilogue", "pv", "s_issue", "tracker", "wg0_warp1", "wg0_warp2", "wg0_warp3"};
+            for (int o = 0; o < 10; ++o)
                 for (int c = 0; c < 32; ++c) {
                     bool any = false;
                     for (int sl = 0; sl < 8; ++sl) any |= hs[(o * 32 + c) * 8 + sl] != 0;

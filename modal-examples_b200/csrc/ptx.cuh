@@ -81,12 +81,33 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 __device__ uint32_t g_attn_prog = 0;  // shared-memory address of the attention kernel's per-role progress words (diagnostics)
 #endif
 
+// try_wait with a suspend-time hint: the waiting thread may stay suspended in hardware for up to `ns` nanoseconds (or until
+// the phase completes) instead of coming back after the default, much shorter, interval.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+
+// Bounded wait: a protocol bug must trap (=> a CUDA error the host reports) instead of hanging the GPU box.  The retry loop
+// asks the hardware to keep the thread suspended for up to 20 us per attempt: ncu showed the single-thread roles' retry loops
+// (try_wait, counter, compare, branch -- ~7 instructions per wake-up at the default suspend time) taking ~20 % of the issue
+// slots of the attention kernel's SM sub-partitions, which they share with the exp warps.  The wall-clock bound is 4 s.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const uint64_t t0 = global_timer_ns();
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 0x3FF) == 0 && global_timer_ns() - t0 > 4000000000ull) {
+    uint64_t t0 = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        const uint64_t now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 4000000000ull) {
             printf("b200rt: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x,
                    (int)threadIdx.x, smem_u32(bar), parity);
 #ifdef B200RT_DIAG

@@ -126,6 +126,12 @@ def main(argv=None):
             out = raw(**kwargs)
             if inspect.isawaitable(out):
                 out = rt.run_maybe_async(lambda: out)
+        if any(f == "--detach" or f == "-d" for f, _ in flags):
+            from .functions import drain_spawned
+
+            n = drain_spawned()
+            if n:
+                print(f"[modal b200] --detach: waited for {n} spawned call(s) to finish")
     if out is not None and isinstance(target, Function):
         print(out)
     return 0

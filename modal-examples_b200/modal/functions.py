@@ -75,6 +75,16 @@ class FunctionCall:
 FunctionCall.gather = _Invokable(FunctionCall._gather, FunctionCall._gather_aio)  # type: ignore[attr-defined]
 
 
+def drain_spawned(timeout=None) -> int:
+    """Block until every `.spawn`ed call of this process has finished (their outcome stays with the handle); returns how many
+    were still running.  `modal run --detach` keeps an app alive until its spawned inputs are done
+    (amazon_embeddings.py:2,17-18,104-116); in-box the CLI waits here before the containers are torn down."""
+    with _calls_lock:
+        pending = [c._future for c in _calls.values() if not c._future.done()]
+    cf.wait(pending, timeout=timeout)
+    return len(pending)
+
+
 def _zip_inputs(iterables):
     if len(iterables) == 1:
         return ((x,) for x in iterables[0])

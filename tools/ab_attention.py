@@ -21,13 +21,13 @@ print(json.dumps(out))
 '''
 res = {"product": [], "exp": []}
 for rep in range(3):
-    for key, lib in (("product", "libb200rt.so"), ("exp", "libb200rt_exp.so")):
+    for key, lib in [("product", "libb200rt.so"), ("exp", "libb200rt_exp.so")] + [(os.path.basename(p)[10:-3], os.path.basename(p)) for p in sorted(__import__("glob").glob(os.path.join(ROOT, "modal-examples_b200", "libb200rt_exp_*.so")))]:
         code = f"ROOT={ROOT!r}\nLIB={os.path.join(ROOT, 'modal-examples_b200', lib)!r}\n" + CHILD
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
         if r.returncode != 0:
             print(key, "FAILED", r.stderr[-1500:])
             continue
-        res[key].append(json.loads(r.stdout.strip().splitlines()[-1]))
+        res.setdefault(key, []).append(json.loads(r.stdout.strip().splitlines()[-1]))
         print(key, res[key][-1], flush=True)
 for k, v in res.items():
     if v:
