@@ -82,6 +82,23 @@ def _install():
     _installed = True
 
 
+# Path-taking entry points of C extensions that bypass ``open``/``os`` and that the reference's scripts call with volume
+# paths: torchvision's file reader / writer behind ``read_image`` / ``write_jpeg`` (image_embeddings_infinity.py:176-186,
+# 318-320).  Wrapped when their module is loaded by the time a mount is registered (scripts import them at module level).
+_FOREIGN = (("torchvision.io.image", "read_file", 0), ("torchvision.io.image", "write_file", 0))
+
+
+def _patch_foreign():
+    import sys
+
+    for mod_name, attr, _pos in _FOREIGN:
+        mod = sys.modules.get(mod_name)
+        fn = getattr(mod, attr, None) if mod is not None else None
+        if fn is not None and not hasattr(fn, "__wrapped__"):
+            _orig[f"{mod_name}.{attr}"] = fn
+            setattr(mod, attr, _wrap(fn))
+
+
 def register(mount_point, local_dir: str) -> bool:
     """Make ``mount_point`` resolve to ``local_dir``.  Returns whether the mount point is usable afterwards."""
     mp = os.path.normpath(str(mount_point))
@@ -107,6 +124,7 @@ def register(mount_point, local_dir: str) -> bool:
     with _lock:
         _mounts[mp] = local_dir
         _install()
+        _patch_foreign()
     return True
 
 

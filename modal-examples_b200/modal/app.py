@@ -5,6 +5,9 @@ from __future__ import annotations
 
 import contextlib
 import inspect
+import json
+import os
+import sys
 
 from . import _runtime as rt
 from .cls import Cls, marks
@@ -14,7 +17,35 @@ from .gpu import parse_gpu_count
 _apps: dict[str, "App"] = {}
 
 
+def _registry_path():
+    from .resources import state_dir
+
+    return os.path.join(state_dir(), "deployed.json")
+
+
+def _read_registry() -> dict:
+    try:
+        with open(_registry_path()) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return {}
+
+
 def _lookup_app(name):
+    """An app of this process, else one that `modal deploy` recorded from another process (`modal deploy x.py` followed by
+    `modal.Cls.from_name(app_name, ...)` in a client script: 06_gpu_and_ml/gpu_snapshot.py:64-77): its file is imported here."""
+    if name in _apps:
+        return _apps[name]
+    ent = _read_registry().get(name)
+    if ent and os.path.exists(ent.get("path", "")):
+        import importlib.util
+
+        mod_name = "_modal_deployed_" + "".join(c if c.isalnum() else "_" for c in name)
+        spec = importlib.util.spec_from_file_location(mod_name, ent["path"])
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[mod_name] = mod
+        sys.path.insert(0, os.path.dirname(ent["path"]))
+        spec.loader.exec_module(mod)
     return _apps.get(name)
 
 
@@ -113,9 +144,23 @@ class App:
 
                 _shutdown_all()
 
-    def deploy(self, **_kw):
+    def deploy(self, *, _source=None, **_kw):
+        """In-process registration plus a record under the state directory so that another process's `from_name` /
+        `lookup` finds the app (the deployed app's code is its source file, re-imported there)."""
         if self.name:
             _apps[self.name] = self
+            src = _source
+            if src is None:
+                f = sys._getframe(1)
+                src = f.f_globals.get("__file__")
+            if src:
+                reg = _read_registry()
+                reg[self.name] = {"path": os.path.abspath(src)}
+                os.makedirs(os.path.dirname(_registry_path()), exist_ok=True)
+                tmp = _registry_path() + f".{os.getpid()}.tmp"
+                with open(tmp, "w") as f:
+                    json.dump(reg, f, indent=1)
+                os.replace(tmp, _registry_path())
         return self
 
     def include(self, other: "App"):

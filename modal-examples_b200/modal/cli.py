@@ -109,8 +109,8 @@ def main(argv=None):
     mod, fn_name = _import_target(rest[0], as_module)
     app = _find_app(mod)
     if verb == "deploy":
-        app.deploy()
-        print(f"[modal b200] deployed app {app.name!r} in-process ({len(app.registered_functions)} functions, {len(app.registered_classes)} classes)")
+        app.deploy(_source=getattr(mod, "__file__", None))
+        print(f"[modal b200] deployed app {app.name!r} ({len(app.registered_functions)} functions, {len(app.registered_classes)} classes)")
         return 0
     if verb == "serve":
         print(f"[modal b200] serve: web endpoints are out of scope in-box; app {app.name!r} imported OK "

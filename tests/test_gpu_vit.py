@@ -101,3 +101,54 @@ def test_scheduler_waves_pool_and_text_model_side_by_side(rt):
     assert model._lib.b200rt_submit(model.handle, one.ctypes.data_as(ctypes.c_void_p), None, 1, 8, o.ctypes.data_as(ctypes.c_void_p), ctypes.byref(t)) == rt.E_INVALID
     with pytest.raises(rt.B200RTError):
         model.submit(np.zeros((1, 3, 32, 32), np.float32))
+
+
+def test_infinity_emb_adapter_matches_the_oracle_on_pil_images(rt, tmp_path):
+    """The product's `infinity_emb` stand-in (what image_embeddings_infinity.py:296-306, 340-350 drives): engines started the
+    reference's way -- several per process, one per concurrent input -- share one loaded model; PIL images go through
+    preprocess.clip_preprocess and the sm_100a tower; vectors equal the oracle's on HF-CLIPImageProcessor pixels.  Weights
+    come from a .safetensors checkpoint in HF CLIP naming (the real-checkpoint path)."""
+    import asyncio
+
+    from b200rt import weights as W
+    from infinity_emb import AsyncEmbeddingEngine, EngineArgs
+    from infinity_emb.primitives import Dtype, InferenceEngine
+    from PIL import Image
+    from transformers import CLIPImageProcessor
+
+    g = C.VitGeometry(layers=2)
+    flat = C.make_weights(g, 4, "trained")
+    ckpt = str(tmp_path / "model.safetensors")
+    W.write_safetensors(ckpt, C.flat_to_hf_state(flat, g))
+    rng = np.random.default_rng(3)
+    # smooth images (JPEG-like statistics); 224 x 224 as the reference's volume holds them, plus two that need resize + crop
+    def img(h, w):
+        base = rng.integers(0, 256, (h // 8 + 1, w // 8 + 1, 3), dtype=np.uint8)
+        return Image.fromarray(base).resize((w, h), Image.BICUBIC)
+
+    images = [img(224, 224) for _ in range(9)] + [img(300, 400), img(512, 260)]
+    args = EngineArgs(model_name_or_path="openai/clip-vit-base-patch16", batch_size=100, model_warmup=False, engine=InferenceEngine.torch,
+                      dtype=Dtype.float16, device="cuda", weights=ckpt)
+
+    async def run():
+        engines = [AsyncEmbeddingEngine.from_args(args) for _ in range(4)]  # n_engines = max_concurrent_inputs (:283-306)
+        for e in engines:
+            await e.astart()
+        outs = await asyncio.gather(*(e.image_embed(images=images) for e in engines))
+        for e in engines:
+            await e.astop()
+        return outs
+
+    outs = asyncio.run(run())
+    assert rt.stats()["items"] > 0  # the fixture's runtime is still up: the adapter did not shut down a pool it does not own
+    proc = CLIPImageProcessor(size={"shortest_edge": 224}, crop_size={"height": 224, "width": 224}, resample=3,
+                              image_mean=[0.48145466, 0.4578275, 0.40821073], image_std=[0.26862954, 0.26130258, 0.27577711])
+    px = proc(images=images, return_tensors="np")["pixel_values"].astype(np.float32)
+    ref = C.forward_np(flat, px, g)
+    first = np.stack(outs[0][0])
+    assert outs[0][1] == len(images) and first.shape == (len(images), g.proj)
+    for vecs, usage in outs[1:]:
+        assert np.array_equal(np.stack(vecs), first)  # same bits from every engine object
+    assert np.abs(np.linalg.norm(first, axis=1) - 1).max() < 1e-5
+    assert C.rel_l2(first[:9], ref[:9]).max() <= 1e-3
+    assert C.rel_l2(first[9:], ref[9:]).max() <= 3e-3  # resized inputs: PIL vs torchvision bicubic differ by <= 1 grey level
