@@ -6,8 +6,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
            --master-port P bench.py --gpus N --steps K --warmup W   # N > 1: one rank per GPU
 
-A "step" is one pass of the hot path over one batch of synthetic input: ITEMS_PER_STEP 512-token items
-per GPU, presented as .map() inputs of 32 items (the reference's BATCH_SIZE,
+A "step" is one pass of the hot path over one batch of synthetic input: 32 waves (32 x 148 = 4736 on a B200;
+BENCH_ITEMS_PER_STEP overrides) of 512-token items per GPU, presented as .map() inputs of 32 items (the reference's BATCH_SIZE,
 06_gpu_and_ml/embeddings/text_embeddings_inference.py:19).  Weak scaling: every rank owns one GPU and an
 equal shard of the items; the path has no data-path collective (items are independent), so ranks only
 meet in the timing barrier.
@@ -36,7 +36,7 @@ sys.path.insert(0, os.path.join(ROOT, "modal-examples_b200"))
 METRIC = "items/sec for BGE-base embed .map()"
 SEQ = 512
 MAP_INPUT_ITEMS = 32           # reference BATCH_SIZE
-ITEMS_PER_STEP = int(os.environ.get("BENCH_ITEMS_PER_STEP", "4096"))  # per GPU
+ITEMS_PER_STEP = int(os.environ.get("BENCH_ITEMS_PER_STEP", "0"))  # per GPU; 0 = 32 waves of the runtime's wave size (32 x 148 = 4736 on a B200)
 REF_ITEMS_PER_STEP = 8         # bounded sample for the CPU arm
 FLOPS_PER_ITEM = 96.64e9       # BASELINE.md §4 (2*m*n*k, all rows, 12 layers)
 
@@ -218,7 +218,7 @@ def run_independent_replicas(args, rank, local_rank, world, barrier, R):
     b200rt.init(devices=[local_rank])
     model = b200rt.EmbedModel(R.geometry_dict(R.BGE_BASE), R.pack_blob(R.make_weights(R.BGE_BASE, 0, "hf"), R.BGE_BASE))
     cap = b200rt.wave_capacity_items()
-    n_step = ITEMS_PER_STEP
+    n_step = ITEMS_PER_STEP or 32 * cap
     with torch.cuda.device(local_rank):
         d_ids = torch.from_numpy(R.synth_ids(n_step, SEQ, seed=rank)).cuda()
         d_lens = torch.full((n_step,), SEQ, dtype=torch.int32, device="cuda")
@@ -287,7 +287,7 @@ def main_ours(args):
         ms, isteps = run_independent_replicas(args, rank, local_rank, world, barrier, R)
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks, device time
-        indep = {"value": isteps * ITEMS_PER_STEP * world / (float(t[0]) / 1e3), "unit": "items/s", "steps": isteps,
+        indep = {"value": isteps * n_step * world / (float(t[0]) / 1e3), "unit": "items/s", "steps": isteps,
                  "what": "one process per GPU, each a 1-replica pool on its own shard, ids resident (no scatter/gather, peer_bytes 0)"}
         torch.cuda.synchronize()
     host_barrier()
@@ -304,7 +304,7 @@ def main_ours(args):
     model = b200rt.EmbedModel(R.geometry_dict(g), R.pack_blob(flat, g))
     del flat
     cap = b200rt.wave_capacity_items()
-    n_step = ITEMS_PER_STEP                      # per GPU
+    n_step = ITEMS_PER_STEP or 32 * cap          # per GPU: 32 full waves, a whole number of 32-item .map() inputs
     n_total = n_step * N                         # per step, whole pool
     ids_host = np.concatenate([R.synth_ids(n_step, SEQ, seed=r) for r in range(N)])  # replica r's shard has seed r
     peaks = load_peaks()

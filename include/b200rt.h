@@ -53,7 +53,7 @@ typedef struct b200rt_stats_t {
 /* Replica pool.  Stands in for `@app.cls(gpu=..., max_containers=N)` + `@modal.concurrent`
  * (text_embeddings_inference.py:79-86): n_gpus local B200s instead of N cloud containers.  Enables peer
  * access between all of them and starts the scheduler threads.  devices = NULL means 0..n_gpus-1.    */
-/* flags: bits 0-15 = items of 512 tokens one replica takes per wave (0 = default 128), see B200RT_INIT_WAVE_ITEMS */
+/* flags: bits 0-15 = items of 512 tokens one replica takes per wave (0 = default: the SM count of the first device, 148 on a B200), see B200RT_INIT_WAVE_ITEMS */
 #define B200RT_INIT_WAVE_ITEMS(n) ((uint32_t)(n) & 0xFFFFu)
 /*        bits 16-23 = k > 0: TWO replicas per GPU; each replica's GEMM launches ask for (SMs - k) SMs and its attention launches
  *        for k, so that one replica's attention (MUFU-bound, light on L2) runs beside the other's GEMMs (L2-fill-bound).       */

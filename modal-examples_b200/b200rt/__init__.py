@@ -121,7 +121,7 @@ _initialised = False
 
 def init(n_gpus: int = 1, devices=None, flags: int = 0, wave_items: int = 0) -> int:
     """Start the replica pool on ``devices`` (default ``0..n_gpus-1``).  Idempotent per process.
-    ``wave_items``: 512-token items one replica takes per wave (0 = the library default, 128)."""
+    ``wave_items``: 512-token items one replica takes per wave (0 = the library default: one per SM, 148 on a B200)."""
     global _initialised
     lib = load_library()
     if _initialised:

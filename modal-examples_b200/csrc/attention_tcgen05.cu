@@ -81,6 +81,10 @@ constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;
 // the reference max follows the true max only when it is exceeded by more than this (raw score units): P <= 2^8
 constexpr float kRescaleThreshold = 8.0f / kScaleLog2e;
 
+#ifdef B200RT_EXP
+#define ATT_P_IN_TMEM 1
+#endif
+
 #ifdef B200RT_DIAG
 // progress dump: every role notes (unit, sub-block, step) in shared memory; a timed-out mbarrier wait prints them all
 #define ATT_PROG(role, u_, c_, step_)                                                                    \
@@ -246,6 +250,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             // short units would start on the second phase of somebody else's slot.  scnt packs, per warpgroup, its S count
             // modulo 4 (bits 4w, 4w+1) and whether it is >= 2 (bit 4w+2).
             uint32_t scnt = 0;
+#ifdef ATT_P_IN_TMEM
+            uint32_t hist0 = 0, hist1 = 0, hist2 = 0, gs_base = 0;  // per warpgroup: running indices of its last two sub-blocks (16 bits each)
+#endif
 #ifdef B200RT_DIAG
             int sdbg = 0;
 #endif
@@ -262,7 +269,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                     if (sb == 0) mbar_wait(&q_full[g & 1], (g >> 1) & 1);
                     if (t == 0 && (sb & 1) == 0) mbar_wait(&k_full[sb >> 1], (k_par >> (sb >> 1)) & 1);  // first touch of the K tile
                     ATT_STAMP(5, sdbg, 1);
+#ifdef ATT_P_IN_TMEM
+                    {   // the slot's previous S became a P in place: reusable once the P.V that reads it has retired
+                        const uint32_t hw = wg == 0 ? hist0 : (wg == 1 ? hist1 : hist2);
+                        if (cw & 4) {
+                            const uint32_t need = (hw >> 16) + 1;
+                            uint32_t v;
+                            do {
+                                asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(retired)) : "memory");
+                            } while (v < need);
+                        }
+                        const uint32_t hn = (hw << 16) | ((gs_base + c) & 0xFFFFu);
+                        if (wg == 0) hist0 = hn; else if (wg == 1) hist1 = hn; else hist2 = hn;
+                    }
+#else
                     if (cw & 4) mbar_wait(&s_free[slot], (((cw >> 1) & 1) ^ 1));                          // the slot's previous S
+#endif
                     tc_fence_after();
                     ATT_STAMP(5, sdbg, 2);
 #pragma unroll
@@ -289,6 +311,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 }
                 k_par ^= (1u << U.nkb) - 1;
                 gt += U.nq;
+#ifdef ATT_P_IN_TMEM
+                gs_base += U.total;
+#endif
             }
         }
       } else if (warp == 2) {
@@ -325,6 +350,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             uint32_t v_par = 0;
             uint32_t gt = 0;
             uint32_t phases = 0;  // bit w: parity of the phase of p_full[w] awaited next
+#ifdef ATT_P_IN_TMEM
+            uint32_t pcnt = 0;    // bit w: parity of the number of sub-blocks warpgroup w has had (== which of its two S slots)
+#else
+            (void)0;
+#endif
 #ifdef B200RT_DIAG
             int gs_dbg = 0;
 #endif
@@ -343,6 +373,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                     if (t == 0 && (sb & 1) == 0) mbar_wait(&v_full[sb >> 1], (v_par >> (sb >> 1)) & 1);
                     tc_fence_after();
                     ATT_STAMP(4, gs_dbg, 1);
+#ifdef ATT_P_IN_TMEM
+                    const uint32_t p_tmem = tmem_base + TM_S + (2 * pb + ((pcnt >> pb) & 1)) * SB;  // P_c sits in its S slot
+                    pcnt ^= 1u << pb;
+#pragma unroll
+                    for (int kk = 0; kk < SB / 16; ++kk) {
+                        const uint32_t bv = v_addr + (sb * SB + kk * 16) * 128;  // key row -> 128 B
+                        umma_f16_ts(tmem_base + TM_O + (g & 1) * D, p_tmem + kk * 8, make_sw128_desc(bv), idesc_o, (sb | kk) != 0);
+                    }
+#else
 #pragma unroll
                     for (int kk = 0; kk < SB / 16; ++kk) {
                         const uint32_t a = p_addr + pb * TILE_BYTES + kk * 32;
@@ -350,6 +389,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                         umma_f16_ss(tmem_base + TM_O + (g & 1) * D, make_sw128_desc(a), make_sw128_desc(bv), idesc_o,
                                     (sb | kk) != 0);
                     }
+#endif
                     umma_commit(&pv_done[pb]);  // P buffer pb is free again; O_t is complete up to sub-block c
                     ATT_STAMP(4, gs_dbg, 2);
 #ifdef B200RT_DIAG
@@ -480,6 +520,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                     tmem_st_wait();
                     load_scores();
                 }
+#ifdef ATT_P_IN_TMEM
+                // P_c overwrites the first 32 columns of its own S slot (this thread's row: loaded above); the S issuer hands
+                // the slot out again only after the P.V that reads P_c has retired
+                const float neg_ms = -m_used * kScaleLog2e;
+                const uint32_t p_tm = tm + TM_S + slot * SB;
+#else
                 tc_fence_before();
                 mbar_arrive(&s_free[slot]);  // the scores live in registers from here on
                 const float neg_ms = -m_used * kScaleLog2e;
@@ -487,8 +533,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 wait_retired(need_own);  // the previous P of this buffer has been consumed
                 if (obs) ATT_PROG(4 + w, u, c, 5);
                 need_own = g + 1;
+#endif
                 if (obs) ATT_STAMP(ow, g, 3);
                 float ls0 = 0.f, ls1 = 0.f;
+#ifdef ATT_P_IN_TMEM
+                uint32_t pk_prev[4];
+#endif
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     uint32_t pk[4];
@@ -502,14 +552,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                         ls1 += p1;
                         pk[e] = pack_half2(p0, p1);
                     }
+#ifdef ATT_P_IN_TMEM
+                    if (q & 1) tmem_st_32x32b_x8(p_tm + (q >> 1) * 8, pk_prev[0], pk_prev[1], pk_prev[2], pk_prev[3], pk[0], pk[1], pk[2], pk[3]);
+                    else { pk_prev[0] = pk[0]; pk_prev[1] = pk[1]; pk_prev[2] = pk[2]; pk_prev[3] = pk[3]; }
+#else
                     // keys 8q .. 8q+7 of row r -> 16-byte chunk q ^ (r & 7) of the row's 128 bytes
                     sts128(p_row + ((static_cast<uint32_t>(q) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
+#endif
                 }
                 l_w += ls0 + ls1;
                 if (sb + NEXP >= U.nsb)  // this warpgroup's last sub-block of the tile
                     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(ls_self + (gtile % MAX_NQ) * (NEXP * QT * 8)), "f"(m_ref), "f"(l_w) : "memory");
+#ifdef ATT_P_IN_TMEM
+                tmem_st_wait();            // P_c is in tensor memory
+                tc_fence_before();         // ... ahead of the MMA that reads it and accumulates into O_t
+#else
                 tc_fence_before();         // our TMEM accesses precede the MMA that accumulates into O_t
                 fence_proxy_async_smem();  // P_c visible to the tensor core's async-proxy reads
+#endif
                 mbar_arrive(&p_full[w]);   // (release: also publishes (m, l) to the epilogue via the o_done chain)
                 if (obs) ATT_PROG(4 + w, u, c, 6);
                 if (obs) ATT_STAMP(ow, g, 4);

@@ -256,7 +256,7 @@ struct Wave {
 
 struct Runtime {
     std::vector<std::unique_ptr<Dev>> devs;
-    int cap_items = 128;  // per replica per wave, at 512 tokens (128 fills the 74 CTA pairs ~10% better than 64)
+    int cap_items = 0;   // per replica per wave, at 512 tokens; 0 = one item per SM of the first device (see rt_init)
     int cap_rows = 0;    // cap_items*512 rounded up to 128
     std::vector<std::unique_ptr<Model>> models;
     // root staging per slot
@@ -972,6 +972,15 @@ int rt_init(const int* devices, int n, uint32_t flags) {
         return fail(B200RT_E_CUDA, "no CUDA device available (%s); b200rt has no CPU path", cudaGetErrorString(e));
     auto rt = std::make_unique<Runtime>();
     if (flags & 0xFFFFu) rt->cap_items = static_cast<int>(flags & 0xFFFFu);  // B200RT_INIT_WAVE_ITEMS(n)
+    if (rt->cap_items == 0) {
+        // Default: as many 512-token items as the GPU has SMs.  A wave of B items is 6B / 18B / 24B pair-GEMM tiles and 12B
+        // attention units, so with B = #SMs (= 2 x CTA pairs) every kernel of the forward runs a whole number of rounds
+        // (148 SMs: 12 / 36 / 48 tiles per pair, 12 units per SM); 128 items left attn-out, FFN2 and attention at 10.4 -> 11
+        // rounds (tools/wave_size_probe.py: 108.3 vs 110.2 us per item).
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, devices ? devices[0] : 0) != cudaSuccess || sms < 2) sms = 128;
+        rt->cap_items = sms & ~1;
+    }
     if (rt->cap_items > 1024) return fail(B200RT_E_INVALID, "wave capacity of %d items per replica is out of range (1..1024)", rt->cap_items);
     rt->cap_rows = ((rt->cap_items * MAX_SEQ + 255) / 256) * 256;
     g_rt = rt.get();  // forward() and friends read capacity through g_rt

@@ -196,6 +196,20 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, ui
         : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (M x 16 halves per instruction: lane = row, 8 consecutive 32-bit columns of
+// packed half2) is read from tensor memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // Arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed.
 // (implies tcgen05.fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -231,6 +245,13 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
           "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]),
           "r"(taddr)
         : "memory");
+}
+
+__device__ __forceinline__ void tmem_st_32x32b_x8(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4,
+                                                  uint32_t r5, uint32_t r6, uint32_t r7) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0, %1, %2, %3, %4, %5, %6, %7};"
+                 ::"r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(r4), "r"(r5), "r"(r6), "r"(r7), "r"(taddr)
+                 : "memory");
 }
 
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
