@@ -150,7 +150,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
     uint64_t* s_full = bars + 24;      // [NSLOT]  S_g landed
     uint64_t* s_free = bars + 30;      // [NSLOT]  S_g is in the exp warpgroup's registers
     uint64_t* p_full = bars + 36;      // [NEXP]  P buffer w written
+#ifdef ATT_P_IN_TMEM
+    uint64_t* pv_done = bars + 36;     // [NSLOT] the P.V reading the P in slot s has retired (p_full[] is not used)
+#else
     uint64_t* pv_done = bars + 39;     // [NEXP]  the P.V reading P buffer w has retired
+#endif
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
     uint32_t* retired = tmem_slot + 1;  // sub-blocks of this CTA whose P.V has retired (written by the tracker thread only)
 #ifdef B200RT_DIAG
@@ -183,10 +187,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             mbar_init(&s_full[i], 1);
             mbar_init(&s_free[i], 128);
         }
+#ifdef ATT_P_IN_TMEM
+        for (int i = 0; i < NSLOT; ++i) mbar_init(&pv_done[i], 1);
+#else
         for (int i = 0; i < NEXP; ++i) {
             mbar_init(&p_full[i], 128);
             mbar_init(&pv_done[i], 1);
         }
+#endif
         *reinterpret_cast<volatile uint32_t*>(retired) = 0;
         fence_barrier_init();
     }
@@ -326,15 +334,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             // reuse of their own P buffer (which also keeps every pv_done[] at most one phase ahead of this thread: a
             // buffer is only refilled once its previous P.V has been counted here) and before touching the accumulator.
             uint32_t phases = 0, g = 0;
+#ifdef ATT_P_IN_TMEM
+            uint32_t tcnt = 0;  // bit w: parity of warpgroup w's sub-block count
+#endif
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const Unit U = decode_unit(u, nq_all, split, lens, S);
                 uint32_t pb = U.c_off;
                 for (int c = 0; c < U.total; ++c) {
                     ATT_PROG(2, u, c, g);
                     ATT_STAMP(6, g, 0);
+#ifdef ATT_P_IN_TMEM
+                    {   // per slot: the slot's next P.V is only issued after this thread has counted the previous one (the S
+                        // issuer hands a slot out again on `retired`), so no barrier gets two phases ahead of its only waiter
+                        const uint32_t tslot = 2 * pb + ((tcnt >> pb) & 1);
+                        tcnt ^= 1u << pb;
+                        mbar_wait(&pv_done[tslot], (phases >> tslot) & 1);
+                        phases ^= 1u << tslot;
+                    }
+#else
                     mbar_wait(&pv_done[pb], (phases >> pb) & 1);
-                    ATT_STAMP(6, g, 1);
                     phases ^= 1u << pb;
+#endif
+                    ATT_STAMP(6, g, 1);
                     ++g;
                     asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(retired)), "r"(g) : "memory");
                     if (++pb == NEXP) pb = 0;
@@ -366,16 +387,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                     const uint32_t g = gt + t;
                     ATT_STAMP(4, gs_dbg, 0);
                     ATT_PROG(3, u, c, pb);
+#ifdef ATT_P_IN_TMEM
+                    // P_c is announced on its SLOT's barrier: a warpgroup may be two sub-blocks ahead of this thread (its two
+                    // slots), so a per-warpgroup barrier could complete two phases before its first wait here
+                    const uint32_t pslot = 2 * pb + ((pcnt >> pb) & 1);
+                    pcnt ^= 1u << pb;
+                    mbar_wait(&s_free[pslot], (phases >> pslot) & 1);
+                    phases ^= 1u << pslot;
+#else
                     mbar_wait(&p_full[pb], (phases >> pb) & 1);
-                    ATT_STAMP(4, gs_dbg, 3);
                     phases ^= 1u << pb;
+#endif
+                    ATT_STAMP(4, gs_dbg, 3);
                     if (sb == 0 && g >= 2) mbar_wait(&o_free[g & 1], ((g >> 1) - 1) & 1);  // tile g-2 has been written out
                     if (t == 0 && (sb & 1) == 0) mbar_wait(&v_full[sb >> 1], (v_par >> (sb >> 1)) & 1);
                     tc_fence_after();
                     ATT_STAMP(4, gs_dbg, 1);
 #ifdef ATT_P_IN_TMEM
-                    const uint32_t p_tmem = tmem_base + TM_S + (2 * pb + ((pcnt >> pb) & 1)) * SB;  // P_c sits in its S slot
-                    pcnt ^= 1u << pb;
+                    const uint32_t p_tmem = tmem_base + TM_S + pslot * SB;  // P_c sits in its S slot
 #pragma unroll
                     for (int kk = 0; kk < SB / 16; ++kk) {
                         const uint32_t bv = v_addr + (sb * SB + kk * 16) * 128;  // key row -> 128 B
@@ -390,7 +419,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                                     (sb | kk) != 0);
                     }
 #endif
+#ifdef ATT_P_IN_TMEM
+                    umma_commit(&pv_done[pslot]);  // the P in this slot has been read; O_t is complete up to sub-block c
+#else
                     umma_commit(&pv_done[pb]);  // P buffer pb is free again; O_t is complete up to sub-block c
+#endif
                     ATT_STAMP(4, gs_dbg, 2);
 #ifdef B200RT_DIAG
                     ++gs_dbg;
@@ -570,7 +603,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 tc_fence_before();         // our TMEM accesses precede the MMA that accumulates into O_t
                 fence_proxy_async_smem();  // P_c visible to the tensor core's async-proxy reads
 #endif
+#ifdef ATT_P_IN_TMEM
+                mbar_arrive(&s_free[slot]);  // "P_c is in slot" (release: also publishes (m, l) to the epilogue via the o_done chain)
+#else
                 mbar_arrive(&p_full[w]);   // (release: also publishes (m, l) to the epilogue via the o_done chain)
+#endif
                 if (obs) ATT_PROG(4 + w, u, c, 6);
                 if (obs) ATT_STAMP(ow, g, 4);
                 sb += NEXP;
