@@ -16,13 +16,18 @@
 // ~660 cycles alone, 1100+ when the same SM sub-partition also issues an accumulator fold (tools/ubench/spin_cost.cu).  So
 // everything that is not the exp is kept off the exp warps:
 //
-//   TMEM         : two 64-column O accumulators (tile parity) + a ring of NSLOT = 6 64-column S slots
+//   TMEM         : two 64-column O accumulators (tile parity) + NSLOT = 6 64-column S slots, two per exp warpgroup.  P_c never
+//                  touches shared memory: the exp warps write it (fp16, 32 columns) over the S_c they have just read and
+//                  the P.V MMA takes its A operand from tensor memory.  (Through a swizzled smem tile -- 8 STS.128 per row, a
+//                  proxy fence, 16 KB written and read back per sub-block -- the launch was 2.2 % slower at full length and
+//                  4.2 % on ragged batches.)
 //   TMA thread   : Q tiles, K / V tiles of this and the next unit (see above)
 //   S thread     : S_c = Q . K_c^T (128x64) into one of the two S slots of the warpgroup that will take sub-block c, as far
-//                  ahead as free slots allow -- across unit boundaries too
-//   P.V thread   : O_t += P_c . V_c accumulates IN TMEM across the tile's sub-blocks (no per-sub-block fold)
+//                  ahead as free slots allow -- across unit boundaries too.  A slot is free again once the P.V that read the
+//                  P in it has RETIRED (the tracker's counter), not when its S has been read.
+//   P.V thread   : O_t += P_c . V_c (A = P_c in TMEM, B = V_c in smem) accumulates IN TMEM across the tile's sub-blocks
 //   3 exp WGs    : warpgroup w takes the sub-blocks of a unit with (c_off + c) % 3 == w, thread = query row: one TMEM read of
-//                  the 64 scores, row max, P_c = exp2((S - m) k) as fp16 into its own 128B-swizzled smem tile, partial row
+//                  the 64 scores, row max, P_c = exp2((S - m) k) as fp16 back into the slot (tcgen05.st), partial row
 //                  sum.  m is the row's RUNNING reference maximum, handed from sub-block to sub-block through shared memory;
 //                  it only moves when the new maximum exceeds it by more than 2^8 in the exp2 domain (P <= 256 is exact
 //                  enough in fp16 and the sums are fp32), so the accumulator in TMEM is rescaled (tcgen05.ld/st by the exp
@@ -51,8 +56,8 @@ constexpr int SB = 64;       // keys per sub-block
 constexpr int D = HEAD_DIM;  // 64
 constexpr int MAX_KB = 4;    // S <= 512
 constexpr int MAX_NQ = 4;
-constexpr int NEXP = 3;      // exp warpgroups == P buffers
-constexpr int NSLOT = 6;     // TMEM S slots of 64 columns
+constexpr int NEXP = 3;      // exp warpgroups
+constexpr int NSLOT = 6;     // TMEM S slots of 64 columns, two per exp warpgroup; P_c (fp16) overwrites the first 32 columns of S_c's
 constexpr uint32_t TM_O = 0;        // accumulators: tile parity -> 2 x 64 columns
 constexpr uint32_t TM_S = 2 * D;    // S ring: NSLOT x 64 columns
 constexpr int TILE_BYTES = 128 * D * 2;  // 16 KB: 128 rows x 128 B
@@ -63,9 +68,8 @@ constexpr int OFF_V = OFF_K + MAX_KB * TILE_BYTES;  // 4 x 16 KB
 constexpr int OFF_MR = OFF_V + MAX_KB * TILE_BYTES; // float [NEXP][128]: reference max after warpgroup w's latest sub-block
 constexpr int OFF_LS = OFF_MR + NEXP * QT * 4;      // float2 [4 tiles in flight][NEXP][128]: (reference max, partial row sum)
 constexpr int OFF_BAR = OFF_LS + MAX_NQ * NEXP * QT * 8;
-constexpr int OFF_P = (OFF_BAR + 512 + 1023) / 1024 * 1024;  // NEXP x 16 KB, 1024-aligned for the 128B swizzle
-static_assert(OFF_P % 1024 == 0 && OFF_V % 1024 == 0, "swizzled tiles must be 1024-byte aligned");
-constexpr int SMEM_BYTES = OFF_P + NEXP * TILE_BYTES + 1024;
+static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0, "swizzled tiles must be 1024-byte aligned");
+constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 constexpr int NUM_THREADS = 128 + NEXP * 128 + 128;  // 640
 static_assert(SMEM_BYTES <= 232448, "shared memory");
 // named barriers 1 .. 9: running-max hand-off, one per (producing warpgroup, consuming warpgroup) pair.  Inside a unit the
@@ -80,10 +84,6 @@ static_assert(BAR_EPI < 16, "named barrier ids");
 constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;
 // the reference max follows the true max only when it is exceeded by more than this (raw score units): P <= 2^8
 constexpr float kRescaleThreshold = 8.0f / kScaleLog2e;
-
-#ifdef B200RT_EXP
-#define ATT_P_IN_TMEM 1
-#endif
 
 #ifdef B200RT_DIAG
 // progress dump: every role notes (unit, sub-block, step) in shared memory; a timed-out mbarrier wait prints them all
@@ -148,13 +148,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
     uint64_t* o_done = bars + 20;      // [2]  the tile's last P.V has retired
     uint64_t* o_free = bars + 22;      // [2]  the epilogue has read the accumulator
     uint64_t* s_full = bars + 24;      // [NSLOT]  S_g landed
-    uint64_t* s_free = bars + 30;      // [NSLOT]  S_g is in the exp warpgroup's registers
-    uint64_t* p_full = bars + 36;      // [NEXP]  P buffer w written
-#ifdef ATT_P_IN_TMEM
-    uint64_t* pv_done = bars + 36;     // [NSLOT] the P.V reading the P in slot s has retired (p_full[] is not used)
-#else
-    uint64_t* pv_done = bars + 39;     // [NEXP]  the P.V reading P buffer w has retired
-#endif
+    uint64_t* p_ready = bars + 30;     // [NSLOT]  P_g has replaced S_g in the slot (all 128 rows)
+    uint64_t* pv_done = bars + 36;     // [NSLOT]  the P.V reading the P in slot s has retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
     uint32_t* retired = tmem_slot + 1;  // sub-blocks of this CTA whose P.V has retired (written by the tracker thread only)
 #ifdef B200RT_DIAG
@@ -185,16 +180,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
         }
         for (int i = 0; i < NSLOT; ++i) {
             mbar_init(&s_full[i], 1);
-            mbar_init(&s_free[i], 128);
+            mbar_init(&p_ready[i], 128);
         }
-#ifdef ATT_P_IN_TMEM
         for (int i = 0; i < NSLOT; ++i) mbar_init(&pv_done[i], 1);
-#else
-        for (int i = 0; i < NEXP; ++i) {
-            mbar_init(&p_full[i], 128);
-            mbar_init(&pv_done[i], 1);
-        }
-#endif
         *reinterpret_cast<volatile uint32_t*>(retired) = 0;
         fence_barrier_init();
     }
@@ -258,9 +246,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             // short units would start on the second phase of somebody else's slot.  scnt packs, per warpgroup, its S count
             // modulo 4 (bits 4w, 4w+1) and whether it is >= 2 (bit 4w+2).
             uint32_t scnt = 0;
-#ifdef ATT_P_IN_TMEM
             uint32_t hist0 = 0, hist1 = 0, hist2 = 0, gs_base = 0;  // per warpgroup: running indices of its last two sub-blocks (16 bits each)
-#endif
 #ifdef B200RT_DIAG
             int sdbg = 0;
 #endif
@@ -277,7 +263,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                     if (sb == 0) mbar_wait(&q_full[g & 1], (g >> 1) & 1);
                     if (t == 0 && (sb & 1) == 0) mbar_wait(&k_full[sb >> 1], (k_par >> (sb >> 1)) & 1);  // first touch of the K tile
                     ATT_STAMP(5, sdbg, 1);
-#ifdef ATT_P_IN_TMEM
                     {   // the slot's previous S became a P in place: reusable once the P.V that reads it has retired
                         const uint32_t hw = wg == 0 ? hist0 : (wg == 1 ? hist1 : hist2);
                         if (cw & 4) {
@@ -290,9 +275,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                         const uint32_t hn = (hw << 16) | ((gs_base + c) & 0xFFFFu);
                         if (wg == 0) hist0 = hn; else if (wg == 1) hist1 = hn; else hist2 = hn;
                     }
-#else
-                    if (cw & 4) mbar_wait(&s_free[slot], (((cw >> 1) & 1) ^ 1));                          // the slot's previous S
-#endif
                     tc_fence_after();
                     ATT_STAMP(5, sdbg, 2);
 #pragma unroll
@@ -319,9 +301,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 }
                 k_par ^= (1u << U.nkb) - 1;
                 gt += U.nq;
-#ifdef ATT_P_IN_TMEM
                 gs_base += U.total;
-#endif
             }
         }
       } else if (warp == 2) {
@@ -334,16 +314,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             // reuse of their own P buffer (which also keeps every pv_done[] at most one phase ahead of this thread: a
             // buffer is only refilled once its previous P.V has been counted here) and before touching the accumulator.
             uint32_t phases = 0, g = 0;
-#ifdef ATT_P_IN_TMEM
             uint32_t tcnt = 0;  // bit w: parity of warpgroup w's sub-block count
-#endif
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const Unit U = decode_unit(u, nq_all, split, lens, S);
                 uint32_t pb = U.c_off;
                 for (int c = 0; c < U.total; ++c) {
                     ATT_PROG(2, u, c, g);
                     ATT_STAMP(6, g, 0);
-#ifdef ATT_P_IN_TMEM
                     {   // per slot: the slot's next P.V is only issued after this thread has counted the previous one (the S
                         // issuer hands a slot out again on `retired`), so no barrier gets two phases ahead of its only waiter
                         const uint32_t tslot = 2 * pb + ((tcnt >> pb) & 1);
@@ -351,10 +328,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                         mbar_wait(&pv_done[tslot], (phases >> tslot) & 1);
                         phases ^= 1u << tslot;
                     }
-#else
-                    mbar_wait(&pv_done[pb], (phases >> pb) & 1);
-                    phases ^= 1u << pb;
-#endif
                     ATT_STAMP(6, g, 1);
                     ++g;
                     asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(retired)), "r"(g) : "memory");
@@ -367,15 +340,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             // ------------------------------------------------------------ P.V issuer: O_t (+)= P_c . V_c
             constexpr uint32_t idesc_o = make_idesc_f16(QT, D, 0, 1);  // 128 x 64, B (= V) MN-major
             const uint32_t v_addr = smem_u32(smem + OFF_V);
-            const uint32_t p_addr = smem_u32(smem + OFF_P);
             uint32_t v_par = 0;
             uint32_t gt = 0;
-            uint32_t phases = 0;  // bit w: parity of the phase of p_full[w] awaited next
-#ifdef ATT_P_IN_TMEM
+            uint32_t phases = 0;  // bit s: parity of the phase of p_ready[s] awaited next
             uint32_t pcnt = 0;    // bit w: parity of the number of sub-blocks warpgroup w has had (== which of its two S slots)
-#else
-            (void)0;
-#endif
 #ifdef B200RT_DIAG
             int gs_dbg = 0;
 #endif
@@ -387,43 +355,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                     const uint32_t g = gt + t;
                     ATT_STAMP(4, gs_dbg, 0);
                     ATT_PROG(3, u, c, pb);
-#ifdef ATT_P_IN_TMEM
                     // P_c is announced on its SLOT's barrier: a warpgroup may be two sub-blocks ahead of this thread (its two
                     // slots), so a per-warpgroup barrier could complete two phases before its first wait here
                     const uint32_t pslot = 2 * pb + ((pcnt >> pb) & 1);
                     pcnt ^= 1u << pb;
-                    mbar_wait(&s_free[pslot], (phases >> pslot) & 1);
+                    mbar_wait(&p_ready[pslot], (phases >> pslot) & 1);
                     phases ^= 1u << pslot;
-#else
-                    mbar_wait(&p_full[pb], (phases >> pb) & 1);
-                    phases ^= 1u << pb;
-#endif
                     ATT_STAMP(4, gs_dbg, 3);
                     if (sb == 0 && g >= 2) mbar_wait(&o_free[g & 1], ((g >> 1) - 1) & 1);  // tile g-2 has been written out
                     if (t == 0 && (sb & 1) == 0) mbar_wait(&v_full[sb >> 1], (v_par >> (sb >> 1)) & 1);
                     tc_fence_after();
                     ATT_STAMP(4, gs_dbg, 1);
-#ifdef ATT_P_IN_TMEM
                     const uint32_t p_tmem = tmem_base + TM_S + pslot * SB;  // P_c sits in its S slot
 #pragma unroll
                     for (int kk = 0; kk < SB / 16; ++kk) {
                         const uint32_t bv = v_addr + (sb * SB + kk * 16) * 128;  // key row -> 128 B
                         umma_f16_ts(tmem_base + TM_O + (g & 1) * D, p_tmem + kk * 8, make_sw128_desc(bv), idesc_o, (sb | kk) != 0);
                     }
-#else
-#pragma unroll
-                    for (int kk = 0; kk < SB / 16; ++kk) {
-                        const uint32_t a = p_addr + pb * TILE_BYTES + kk * 32;
-                        const uint32_t bv = v_addr + (sb * SB + kk * 16) * 128;  // key row -> 128 B
-                        umma_f16_ss(tmem_base + TM_O + (g & 1) * D, make_sw128_desc(a), make_sw128_desc(bv), idesc_o,
-                                    (sb | kk) != 0);
-                    }
-#endif
-#ifdef ATT_P_IN_TMEM
                     umma_commit(&pv_done[pslot]);  // the P in this slot has been read; O_t is complete up to sub-block c
-#else
-                    umma_commit(&pv_done[pb]);  // P buffer pb is free again; O_t is complete up to sub-block c
-#endif
                     ATT_STAMP(4, gs_dbg, 2);
 #ifdef B200RT_DIAG
                     ++gs_dbg;
@@ -449,7 +398,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
         const int wp = (w + NEXP - 1) % NEXP;  // the warpgroup that handles c - 1 inside a unit
         const int r = (warp & 3) * 32 + lane;  // query row within the tile == TMEM lane
         const uint32_t tm = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-        const uint32_t p_row = smem_u32(smem + OFF_P + w * TILE_BYTES) + r * 128;
         const uint32_t mr_base = smem_u32(smem + OFF_MR) + r * 4;
         const uint32_t mr_self = mr_base + w * QT * 4;
         const uint32_t ls_self = smem_u32(smem + OFF_LS) + (w * QT + r) * 8;
@@ -457,7 +405,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
         const bool obs = lane == 0 && ((warp & 3) == 0 || w == 0);
         const int ow = (warp & 3) == 0 ? w : 6 + (warp & 3);  // observer row: warp 0 of every warpgroup, all warps of warpgroup 0
         (void)obs; (void)ow;
-        uint32_t need_own = 0;                // 1 + the running index of this warpgroup's previous sub-block (0: none yet)
         uint32_t scnt = 0;                    // sub-blocks this warpgroup has taken so far
         const uint32_t retired_addr = smem_u32(retired);
         auto wait_retired = [&](uint32_t n) {  // until the P.V of the CTA's first n sub-blocks have retired
@@ -553,25 +500,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                     tmem_st_wait();
                     load_scores();
                 }
-#ifdef ATT_P_IN_TMEM
                 // P_c overwrites the first 32 columns of its own S slot (this thread's row: loaded above); the S issuer hands
                 // the slot out again only after the P.V that reads P_c has retired
                 const float neg_ms = -m_used * kScaleLog2e;
                 const uint32_t p_tm = tm + TM_S + slot * SB;
-#else
-                tc_fence_before();
-                mbar_arrive(&s_free[slot]);  // the scores live in registers from here on
-                const float neg_ms = -m_used * kScaleLog2e;
-                if (obs) ATT_PROG(4 + w, u, c, 4 + 16 * need_own);
-                wait_retired(need_own);  // the previous P of this buffer has been consumed
-                if (obs) ATT_PROG(4 + w, u, c, 5);
-                need_own = g + 1;
-#endif
                 if (obs) ATT_STAMP(ow, g, 3);
                 float ls0 = 0.f, ls1 = 0.f;
-#ifdef ATT_P_IN_TMEM
                 uint32_t pk_prev[4];
-#endif
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     uint32_t pk[4];
@@ -585,29 +520,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                         ls1 += p1;
                         pk[e] = pack_half2(p0, p1);
                     }
-#ifdef ATT_P_IN_TMEM
                     if (q & 1) tmem_st_32x32b_x8(p_tm + (q >> 1) * 8, pk_prev[0], pk_prev[1], pk_prev[2], pk_prev[3], pk[0], pk[1], pk[2], pk[3]);
                     else { pk_prev[0] = pk[0]; pk_prev[1] = pk[1]; pk_prev[2] = pk[2]; pk_prev[3] = pk[3]; }
-#else
-                    // keys 8q .. 8q+7 of row r -> 16-byte chunk q ^ (r & 7) of the row's 128 bytes
-                    sts128(p_row + ((static_cast<uint32_t>(q) ^ swz) << 4), pk[0], pk[1], pk[2], pk[3]);
-#endif
                 }
                 l_w += ls0 + ls1;
                 if (sb + NEXP >= U.nsb)  // this warpgroup's last sub-block of the tile
                     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(ls_self + (gtile % MAX_NQ) * (NEXP * QT * 8)), "f"(m_ref), "f"(l_w) : "memory");
-#ifdef ATT_P_IN_TMEM
                 tmem_st_wait();            // P_c is in tensor memory
                 tc_fence_before();         // ... ahead of the MMA that reads it and accumulates into O_t
-#else
-                tc_fence_before();         // our TMEM accesses precede the MMA that accumulates into O_t
-                fence_proxy_async_smem();  // P_c visible to the tensor core's async-proxy reads
-#endif
-#ifdef ATT_P_IN_TMEM
-                mbar_arrive(&s_free[slot]);  // "P_c is in slot" (release: also publishes (m, l) to the epilogue via the o_done chain)
-#else
-                mbar_arrive(&p_full[w]);   // (release: also publishes (m, l) to the epilogue via the o_done chain)
-#endif
+                mbar_arrive(&p_ready[slot]);  // (release: also publishes (m, l) to the epilogue via the o_done chain)
                 if (obs) ATT_PROG(4 + w, u, c, 6);
                 if (obs) ATT_STAMP(ow, g, 4);
                 sb += NEXP;
