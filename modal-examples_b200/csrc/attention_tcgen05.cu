@@ -132,7 +132,8 @@ __device__ __forceinline__ Unit decode_unit(int u, int nq_all, int split, const 
 }
 
 // 640 threads (96 registers each at launch); the warpgroups re-balance WITHIN that pool of 640 x 96: 120 for the exp warps,
-// 80 for the epilogue, 40 for the rest (asking for more than the launch allocation holds makes setmaxnreg.inc spin forever).
+// 64 for the epilogue, 56 for the single-thread roles (their loops pace the kernel: no spills there);
+// (asking for more than the launch allocation holds makes setmaxnreg.inc spin forever).
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tctx,
                  const int32_t* __restrict__ lens, int S, int split, int n_units, unsigned long long* __restrict__ dbg) {
@@ -152,6 +153,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
     uint64_t* pv_done = bars + 36;     // [NSLOT]  the P.V reading the P in slot s has retired
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
     uint32_t* retired = tmem_slot + 1;  // sub-blocks of this CTA whose P.V has retired (written by the tracker thread only)
+    uint32_t* slot_need = tmem_slot + 36;  // [NSLOT] 1 + index of the slot's last sub-block (S issuer's own bookkeeping)
 #ifdef B200RT_DIAG
     uint32_t* prog = tmem_slot + 4;     // [8 roles][4]
     g_attn_prog = smem_u32(prog);
@@ -184,6 +186,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
         }
         for (int i = 0; i < NSLOT; ++i) mbar_init(&pv_done[i], 1);
         *reinterpret_cast<volatile uint32_t*>(retired) = 0;
+        for (int i = 0; i < NSLOT; ++i) reinterpret_cast<volatile uint32_t*>(slot_need)[i] = 0;
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -194,7 +197,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
 
     // (each role's code must be dominated by its own setmaxnreg for ptxas to allocate against the new budget)
     if (warp < 4) {
-      setmaxnreg_dec<40>();
+      setmaxnreg_dec<56>();
       if (warp == 0) {
         if (elect_one()) {
             // ------------------------------------------------------------ TMA producer
@@ -235,73 +238,77 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
       } else if (warp == 1) {
         if (elect_one()) {
             // ------------------------------------------------------------ S issuer: S_c = Q . K_c^T
-            constexpr uint32_t idesc_s = make_idesc_f16(QT, SB);  // 128 x 64, both K-major
-            const uint32_t q_addr = smem_u32(smem + OFF_Q);
-            const uint32_t k_addr = smem_u32(smem + OFF_K);
-            uint32_t k_par = 0;  // bit j: parity of the number of units that used K tile j so far
-            uint32_t gt = 0;        // running query-tile index
+            // This thread's instruction stream paces the kernel once everything else overlaps (ncu: 130 instructions per
+            // sub-block at ~7 cycles each made it the bottleneck), so the loop is nested by (unit, tile, sub-block) with
+            // everything that can be hoisted hoisted: descriptor low words are running sums (a 128B-swizzled tile address
+            // enters the descriptor as addr >> 4, so +32 bytes along K is +2 and one 64-key sub-block is +512), the slot
+            // bookkeeping is one bit per warpgroup and one shared-memory word per slot.
+            //
             // S slots belong to warpgroups: warpgroup w consumes S slots 2w and 2w+1 alternately.  A barrier must have ONE
             // waiter that meets its phases in order (a first wait for phase 1 of a barrier whose phase 0 the waiter never saw
             // passes at once): with slots handed out by the running sub-block index, a warpgroup that sat out the CTA's first
-            // short units would start on the second phase of somebody else's slot.  scnt packs, per warpgroup, its S count
-            // modulo 4 (bits 4w, 4w+1) and whether it is >= 2 (bit 4w+2).
-            uint32_t scnt = 0;
-            uint32_t hist0 = 0, hist1 = 0, hist2 = 0, gs_base = 0;  // per warpgroup: running indices of its last two sub-blocks (16 bits each)
+            // short units would start on the second phase of somebody else's slot.
+            // A slot is free again once the P.V that read the P in it has RETIRED: slot_need[s] is 1 + the CTA-wide index of
+            // the sub-block that used slot s last (0: never used), compared with the tracker's counter.
+            constexpr uint32_t idesc_s = make_idesc_f16(QT, SB);  // 128 x 64, both K-major
+            constexpr uint32_t kDescHi = static_cast<uint32_t>(make_sw128_desc(0) >> 32);
+            const uint32_t q_lo0 = static_cast<uint32_t>(make_sw128_desc(smem_u32(smem + OFF_Q)));
+            const uint32_t k_lo0 = static_cast<uint32_t>(make_sw128_desc(smem_u32(smem + OFF_K)));
+            const uint32_t need_addr = smem_u32(slot_need);
+            const uint32_t retired_addr = smem_u32(retired);
+            uint32_t k_par = 0;  // bit j: parity of the number of units that used K tile j so far
+            uint32_t par = 0;    // bit w: which of its two slots warpgroup w takes next
+            uint32_t gt = 0;     // running query-tile index
+            uint32_t gidx = 0;   // running sub-block index
 #ifdef B200RT_DIAG
             int sdbg = 0;
 #endif
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const Unit U = decode_unit(u, nq_all, split, lens, S);
-                int t = 0, sb = 0;
                 uint32_t wg = U.c_off;
-                for (int c = 0; c < U.total; ++c) {  // runs as far ahead as free slots allow
-                    const uint32_t cw = (scnt >> (4 * wg)) & 7;        // this warpgroup's count: low two bits + ">= 2"
-                    const uint32_t slot = 2 * wg + (cw & 1);
+                for (int t = 0; t < U.nq; ++t) {
                     const uint32_t g = gt + t;
-                    ATT_PROG(1, u, c, slot);
-                    ATT_STAMP(5, sdbg, 0);
-                    if (sb == 0) mbar_wait(&q_full[g & 1], (g >> 1) & 1);
-                    if (t == 0 && (sb & 1) == 0) mbar_wait(&k_full[sb >> 1], (k_par >> (sb >> 1)) & 1);  // first touch of the K tile
-                    ATT_STAMP(5, sdbg, 1);
-                    {   // the slot's previous S became a P in place: reusable once the P.V that reads it has retired
-                        const uint32_t hw = wg == 0 ? hist0 : (wg == 1 ? hist1 : hist2);
-                        if (cw & 4) {
-                            const uint32_t need = (hw >> 16) + 1;
-                            uint32_t v;
+                    mbar_wait(&q_full[g & 1], (g >> 1) & 1);
+                    const uint32_t q_lo = q_lo0 + (g & 1) * (TILE_BYTES >> 4);
+                    uint32_t k_lo = k_lo0;
+                    const bool first = t == 0, last = t == U.nq - 1;
+                    for (int sb = 0; sb < U.nsb; ++sb) {  // runs as far ahead as free slots allow
+                        const uint32_t slot = 2 * wg + ((par >> wg) & 1);
+                        par ^= 1u << wg;
+                        ATT_PROG(1, u, t * U.nsb + sb, slot);
+                        ATT_STAMP(5, sdbg, 0);
+                        if (first && (sb & 1) == 0) mbar_wait(&k_full[sb >> 1], (k_par >> (sb >> 1)) & 1);  // first touch of the K tile
+                        ATT_STAMP(5, sdbg, 1);
+                        {
+                            uint32_t need, v;
+                            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(need) : "r"(need_addr + slot * 4) : "memory");
                             do {
-                                asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(smem_u32(retired)) : "memory");
+                                asm volatile("ld.acquire.cta.shared.b32 %0, [%1];" : "=r"(v) : "r"(retired_addr) : "memory");
                             } while (v < need);
                         }
-                        const uint32_t hn = (hw << 16) | ((gs_base + c) & 0xFFFFu);
-                        if (wg == 0) hist0 = hn; else if (wg == 1) hist1 = hn; else hist2 = hn;
-                    }
-                    tc_fence_after();
-                    ATT_STAMP(5, sdbg, 2);
+                        tc_fence_after();
+                        ATT_STAMP(5, sdbg, 2);
+                        const uint32_t d_tmem = tmem_base + TM_S + slot * SB;
 #pragma unroll
-                    for (int k = 0; k < D / 16; ++k) {
-                        umma_f16_ss(tmem_base + TM_S + slot * SB, make_sw128_desc(q_addr + (g & 1) * TILE_BYTES + k * 32),
-                                    make_sw128_desc(k_addr + sb * (SB * 128) + k * 32), idesc_s, k != 0);
-                    }
-                    umma_commit(&s_full[slot]);
-                    ATT_STAMP(5, sdbg, 3);
+                        for (int k = 0; k < D / 16; ++k) {
+                            umma_f16_ss(d_tmem, (static_cast<uint64_t>(kDescHi) << 32) | (q_lo + 2 * k),
+                                        (static_cast<uint64_t>(kDescHi) << 32) | (k_lo + 2 * k), idesc_s, k != 0);
+                        }
+                        umma_commit(&s_full[slot]);
+                        ++gidx;
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(need_addr + slot * 4), "r"(gidx) : "memory");
+                        ATT_STAMP(5, sdbg, 3);
 #ifdef B200RT_DIAG
-                    ++sdbg;
+                        ++sdbg;
 #endif
-                    // the unit's last tile is through with K tile j after its odd sub-block (or the last one): free it
-                    if (t == U.nq - 1 && ((sb & 1) == 1 || sb == U.nsb - 1)) umma_commit(&k_free[sb >> 1]);
-                    {   // count: (low two bits + 1) mod 4, sticky ">= 2"
-                        const uint32_t lo = ((cw & 3) + 1) & 3, ge2 = (cw & 4) | ((cw & 3) >= 1 ? 4u : 0u);
-                        scnt = (scnt & ~(7u << (4 * wg))) | ((lo | ge2) << (4 * wg));
-                    }
-                    if (++wg == NEXP) wg = 0;
-                    if (++sb == U.nsb) {
-                        sb = 0;
-                        ++t;
+                        // the unit's last tile is through with K tile j after its odd sub-block (or the last one): free it
+                        if (last && ((sb & 1) == 1 || sb == U.nsb - 1)) umma_commit(&k_free[sb >> 1]);
+                        k_lo += (SB * 128) >> 4;
+                        wg = wg == NEXP - 1 ? 0 : wg + 1;
                     }
                 }
                 k_par ^= (1u << U.nkb) - 1;
                 gt += U.nq;
-                gs_base += U.total;
             }
         }
       } else if (warp == 2) {
@@ -310,81 +317,83 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
             // The ONLY waiter on pv_done[]: it meets every phase of every one of them in the CTA's sub-block order and
             // publishes the count of retired sub-blocks.  mbarrier parity waits are only sound for a waiter that can be at
             // most one phase behind; the exp warpgroups are not (after a unit boundary the sub-block a rescale depends on may
-            // belong to a warpgroup whose previous P.V they never waited for), so they read this counter instead -- for the
-            // reuse of their own P buffer (which also keeps every pv_done[] at most one phase ahead of this thread: a
-            // buffer is only refilled once its previous P.V has been counted here) and before touching the accumulator.
+            // belong to a warpgroup whose previous P.V they never waited for), so they read this counter instead before
+            // touching the accumulator, and the S issuer reads it before handing a slot out again -- which also keeps every
+            // pv_done[] (one per slot) at most one phase ahead of this thread.
+            const uint32_t retired_addr = smem_u32(retired);
             uint32_t phases = 0, g = 0;
-            uint32_t tcnt = 0;  // bit w: parity of warpgroup w's sub-block count
+            uint32_t par = 0;  // bit w: parity of warpgroup w's sub-block count (== which of its two slots)
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const Unit U = decode_unit(u, nq_all, split, lens, S);
                 uint32_t pb = U.c_off;
                 for (int c = 0; c < U.total; ++c) {
                     ATT_PROG(2, u, c, g);
                     ATT_STAMP(6, g, 0);
-                    {   // per slot: the slot's next P.V is only issued after this thread has counted the previous one (the S
-                        // issuer hands a slot out again on `retired`), so no barrier gets two phases ahead of its only waiter
-                        const uint32_t tslot = 2 * pb + ((tcnt >> pb) & 1);
-                        tcnt ^= 1u << pb;
-                        mbar_wait(&pv_done[tslot], (phases >> tslot) & 1);
-                        phases ^= 1u << tslot;
-                    }
+                    const uint32_t tslot = 2 * pb + ((par >> pb) & 1);
+                    par ^= 1u << pb;
+                    mbar_wait(&pv_done[tslot], (phases >> tslot) & 1);
+                    phases ^= 1u << tslot;
                     ATT_STAMP(6, g, 1);
                     ++g;
-                    asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(smem_u32(retired)), "r"(g) : "memory");
-                    if (++pb == NEXP) pb = 0;
+                    asm volatile("st.release.cta.shared.b32 [%0], %1;" ::"r"(retired_addr), "r"(g) : "memory");
+                    pb = pb == NEXP - 1 ? 0 : pb + 1;
                 }
             }
         }
       } else if (warp == 3) {
         if (elect_one()) {
             // ------------------------------------------------------------ P.V issuer: O_t (+)= P_c . V_c
+            // (same lean loop structure as the S issuer; A = P_c in tensor memory, 8 columns per 16-key step; B = V_c: one
+            // key row is 128 B, so 16 keys are +128 in the descriptor's address field and a 64-key sub-block +512)
             constexpr uint32_t idesc_o = make_idesc_f16(QT, D, 0, 1);  // 128 x 64, B (= V) MN-major
-            const uint32_t v_addr = smem_u32(smem + OFF_V);
+            constexpr uint32_t kDescHi = static_cast<uint32_t>(make_sw128_desc(0) >> 32);
+            const uint32_t v_lo0 = static_cast<uint32_t>(make_sw128_desc(smem_u32(smem + OFF_V)));
             uint32_t v_par = 0;
             uint32_t gt = 0;
             uint32_t phases = 0;  // bit s: parity of the phase of p_ready[s] awaited next
-            uint32_t pcnt = 0;    // bit w: parity of the number of sub-blocks warpgroup w has had (== which of its two S slots)
+            uint32_t par = 0;     // bit w: parity of the number of sub-blocks warpgroup w has had (== which of its two S slots)
 #ifdef B200RT_DIAG
             int gs_dbg = 0;
 #endif
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 const Unit U = decode_unit(u, nq_all, split, lens, S);
-                int t = 0, sb = 0;
                 uint32_t pb = U.c_off;
-                for (int c = 0; c < U.total; ++c) {
+                for (int t = 0; t < U.nq; ++t) {
                     const uint32_t g = gt + t;
-                    ATT_STAMP(4, gs_dbg, 0);
-                    ATT_PROG(3, u, c, pb);
-                    // P_c is announced on its SLOT's barrier: a warpgroup may be two sub-blocks ahead of this thread (its two
-                    // slots), so a per-warpgroup barrier could complete two phases before its first wait here
-                    const uint32_t pslot = 2 * pb + ((pcnt >> pb) & 1);
-                    pcnt ^= 1u << pb;
-                    mbar_wait(&p_ready[pslot], (phases >> pslot) & 1);
-                    phases ^= 1u << pslot;
-                    ATT_STAMP(4, gs_dbg, 3);
-                    if (sb == 0 && g >= 2) mbar_wait(&o_free[g & 1], ((g >> 1) - 1) & 1);  // tile g-2 has been written out
-                    if (t == 0 && (sb & 1) == 0) mbar_wait(&v_full[sb >> 1], (v_par >> (sb >> 1)) & 1);
-                    tc_fence_after();
-                    ATT_STAMP(4, gs_dbg, 1);
-                    const uint32_t p_tmem = tmem_base + TM_S + pslot * SB;  // P_c sits in its S slot
+                    const uint32_t d_tmem = tmem_base + TM_O + (g & 1) * D;
+                    uint32_t v_lo = v_lo0;
+                    const bool first = t == 0, last = t == U.nq - 1;
+                    for (int sb = 0; sb < U.nsb; ++sb) {
+                        ATT_STAMP(4, gs_dbg, 0);
+                        ATT_PROG(3, u, t * U.nsb + sb, pb);
+                        // P_c is announced on its SLOT's barrier: a warpgroup may be two sub-blocks ahead of this thread (its
+                        // two slots), so a per-warpgroup barrier could complete two phases before its first wait here
+                        const uint32_t pslot = 2 * pb + ((par >> pb) & 1);
+                        par ^= 1u << pb;
+                        mbar_wait(&p_ready[pslot], (phases >> pslot) & 1);
+                        phases ^= 1u << pslot;
+                        ATT_STAMP(4, gs_dbg, 3);
+                        if (sb == 0 && g >= 2) mbar_wait(&o_free[g & 1], ((g >> 1) - 1) & 1);  // tile g-2 has been written out
+                        if (first && (sb & 1) == 0) mbar_wait(&v_full[sb >> 1], (v_par >> (sb >> 1)) & 1);
+                        tc_fence_after();
+                        ATT_STAMP(4, gs_dbg, 1);
+                        const uint32_t p_tmem = tmem_base + TM_S + pslot * SB;  // P_c sits in its S slot
 #pragma unroll
-                    for (int kk = 0; kk < SB / 16; ++kk) {
-                        const uint32_t bv = v_addr + (sb * SB + kk * 16) * 128;  // key row -> 128 B
-                        umma_f16_ts(tmem_base + TM_O + (g & 1) * D, p_tmem + kk * 8, make_sw128_desc(bv), idesc_o, (sb | kk) != 0);
-                    }
-                    umma_commit(&pv_done[pslot]);  // the P in this slot has been read; O_t is complete up to sub-block c
-                    ATT_STAMP(4, gs_dbg, 2);
+                        for (int kk = 0; kk < SB / 16; ++kk) {
+                            umma_f16_ts(d_tmem, p_tmem + kk * 8, (static_cast<uint64_t>(kDescHi) << 32) | (v_lo + kk * ((16 * 128) >> 4)),
+                                        idesc_o, (sb | kk) != 0);
+                        }
+                        umma_commit(&pv_done[pslot]);  // the P in this slot has been read; O_t is complete up to sub-block c
+                        ATT_STAMP(4, gs_dbg, 2);
 #ifdef B200RT_DIAG
-                    ++gs_dbg;
+                        ++gs_dbg;
 #endif
-                    if (t == U.nq - 1 && ((sb & 1) == 1 || sb == U.nsb - 1)) umma_commit(&v_free[sb >> 1]);
-                    if (++sb == U.nsb) {
-                        umma_commit(&o_done[g & 1]);
-                        sb = 0;
-                        ++t;
+                        if (last && ((sb & 1) == 1 || sb == U.nsb - 1)) umma_commit(&v_free[sb >> 1]);
+                        if (sb == U.nsb - 1) umma_commit(&o_done[g & 1]);
+                        v_lo += (SB * 128) >> 4;
+                        pb = pb == NEXP - 1 ? 0 : pb + 1;
+                        ATT_STAMP(4, gs_dbg - 1, 4);
                     }
-                    if (++pb == NEXP) pb = 0;
-                    ATT_STAMP(4, gs_dbg - 1, 4);
                 }
                 v_par ^= (1u << U.nkb) - 1;
                 gt += U.nq;
@@ -544,7 +553,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
         }
     } else {
         // ---------------------------------------------------------------- epilogue warpgroup: ctx = O_t / l
-        setmaxnreg_dec<80>();
+        setmaxnreg_dec<64>();
         const int r = (warp & 3) * 32 + lane;
         const uint32_t tm = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
         const uint32_t ls_base = smem_u32(smem + OFF_LS) + r * 8;

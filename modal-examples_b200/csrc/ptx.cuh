@@ -103,10 +103,18 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
 // slots of the attention kernel's SM sub-partitions, which they share with the exp warps.  The wall-clock bound is 4 s.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
+    // retry loop: suspended in hardware for up to 20 us per attempt; the wall clock is only looked at every 256th wake-up
+    // (single-thread roles run this loop once per sub-block: ~15 instructions per wake-up for timer arithmetic were a
+    // measurable share of their instruction budget)
     uint64_t t0 = 0;
+    uint32_t spins = 0;
     while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if ((++spins & 0xFFu) != 0) continue;
         const uint64_t now = global_timer_ns();
-        if (t0 == 0) t0 = now;
+        if (t0 == 0) {
+            t0 = now;
+            continue;
+        }
         if (now - t0 > 4000000000ull) {
             printf("b200rt: mbarrier wait timed out (block %d thread %d bar@%u parity %u)\n", (int)blockIdx.x,
                    (int)threadIdx.x, smem_u32(bar), parity);
@@ -343,8 +351,8 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
 // bytes run along K) and for MN-major operands (row = K index, the 128 bytes run along N);
 // the major-ness itself is in the instruction descriptor.
 // bits [0,14) addr>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes = 16,
-                                                    uint32_t sbo_bytes = 1024) {
+__host__ __device__ constexpr uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes = 16,
+                                                       uint32_t sbo_bytes = 1024) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
