@@ -244,7 +244,7 @@ def run_independent_replicas(args, rank, local_rank, world, barrier, R):
     del d_ids, d_lens, d_out
     b200rt.shutdown()
     torch.cuda.empty_cache()
-    return ms, steps
+    return ms, steps, n_step
 
 
 def main_ours(args):
@@ -284,10 +284,10 @@ def main_ours(args):
     # ---------------- N > 1, secondary: independent 1-replica pools, one per rank (the round-1 deployment)
     indep = None
     if use_dist:
-        ms, isteps = run_independent_replicas(args, rank, local_rank, world, barrier, R)
+        ms, isteps, istep_items = run_independent_replicas(args, rank, local_rank, world, barrier, R)
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks, device time
-        indep = {"value": isteps * n_step * world / (float(t[0]) / 1e3), "unit": "items/s", "steps": isteps,
+        indep = {"value": isteps * istep_items * world / (float(t[0]) / 1e3), "unit": "items/s", "steps": isteps,
                  "what": "one process per GPU, each a 1-replica pool on its own shard, ids resident (no scatter/gather, peer_bytes 0)"}
         torch.cuda.synchronize()
     host_barrier()

@@ -30,7 +30,10 @@ def random_blob(seed: int = 0):
 
 
 @app.cls(gpu="B200:8", max_containers=1)
-@modal.concurrent(max_inputs=64)  # batches in flight; the C++ scheduler coalesces them into waves
+# Batches in flight; the C++ scheduler coalesces them into waves.  The reference allows 20 containers x 10 inputs = 200
+# (text_embeddings_inference.py:79-86); one wave of the 8-replica pool is 8 x 148 items = 37 batches of 32 and the scheduler
+# wants two to three waves' worth of tickets pending, hence 96 (each a thread blocked in b200rt_wait with the GIL released).
+@modal.concurrent(max_inputs=96)
 class TextEmbeddings:
     weights: str = modal.parameter(default="")
     n_gpus: int = modal.parameter(default=0)
