@@ -601,7 +601,7 @@ def main_ours(args):
                 "ms_per_step": e2e_s / args.steps * 1e3,
                 "api": "b200rt_submit_ex(BORROW_IDS)/b200rt_wait (C ABI; ids and out in b200rt_alloc_pinned memory, DMA'd in place)",
                 "device_resident_rerun_after_e2e": total_items / (dev_ms_after / 1e3),
-                "per_step_ms": {k: (s1[k] - s0[k]) / args.steps / 1e3 for k in ("stage_us", "dispatch_us", "h2d_scatter_us", "forward_us", "gap_us", "d2h_us")}},
+                "per_step_ms": {k: (s1[k] - s0[k]) / args.steps / 1e3 for k in ("stage_us", "dispatch_us", "h2d_scatter_us", "forward_us", "gap_us", "d2h_us", "forward_max_us", "gap_max_us")}},
         "e2e_map": e2e_map, "ragged": ragged, "secondary_clip_vit": vit,
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
         "latency": {"p50_ms": p50_ms, "p99_ms": p99_ms, "what": "one 512-token item, b200rt_submit_ex+b200rt_wait, pinned host buffers, 1000 trials after 100 warm-ups",

@@ -48,6 +48,8 @@ typedef struct b200rt_stats_t {
     double stage_us, h2d_scatter_us, forward_us, d2h_us; /* summed per-wave stage times (device events; forward = root replica) */
     double gap_us;                      /* idle time of the first participating replica's compute stream between consecutive waves */
     double dispatch_us;                 /* host time the dispatcher spent forming, staging and enqueueing waves */
+    double forward_max_us;              /* summed per wave: the slowest participating replica's forward (device events) */
+    double gap_max_us;                  /* summed per wave: the largest idle time any participating replica's compute stream had before it */
 } b200rt_stats_t;
 
 /* Replica pool.  Stands in for `@app.cls(gpu=..., max_containers=N)` + `@modal.concurrent`

@@ -49,7 +49,7 @@ class VitConfig(ctypes.Structure):
 
 class Stats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ("items", "waves", "tickets", "kernel_launches", "h2d_bytes", "d2h_bytes", "peer_bytes")] + [
-        (n, ctypes.c_double) for n in ("stage_us", "h2d_scatter_us", "forward_us", "d2h_us", "gap_us", "dispatch_us")
+        (n, ctypes.c_double) for n in ("stage_us", "h2d_scatter_us", "forward_us", "d2h_us", "gap_us", "dispatch_us", "forward_max_us", "gap_max_us")
     ]
 
     def as_dict(self):

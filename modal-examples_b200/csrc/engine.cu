@@ -194,6 +194,7 @@ struct Dev {
     CUtensorMap m_im2col;          // vit: the ffn buffer viewed as the im2col matrix [rows, 768]
     cudaEvent_t ev_done[NSLOT];
     cudaEvent_t ev_begin[NSLOT], ev_end[NSLOT];  // timing: the forward itself on this replica's compute stream
+    int last_slot = -1;                          // completer only: slot of this replica's previous wave (gap statistics)
     std::mutex mu;  // serialises host-side enqueue on this replica (scheduler vs. embed_device/debug)
     // Every forward on this replica uses the same workspace (yhi, ylo, qkv, ctx, ffn, pstats), whichever stream it is
     // enqueued on: ev_ws is recorded behind each forward and waited on ahead of the next one, so forwards from the
@@ -249,6 +250,7 @@ struct Wave {
     int slot;
     int n_items, S;
     int first_dev = 0;        // lowest replica that took part (its events time the forward)
+    uint32_t dev_mask = 0;    // replicas that took part
     bool direct_h2d = false;  // some segments were DMA'd from caller-pinned memory
     int out_dim = HIDDEN;     // floats per result row
     std::vector<Segment> segs;
@@ -736,6 +738,7 @@ void dispatcher_main(Runtime* rtp) {
         for (int g = 0; g < G; ++g) {
             if (plan.item_count[g] == 0) continue;
             if (wv.first_dev < 0) wv.first_dev = g;
+            wv.dev_mask |= 1u << g;
             Dev& d = *rt.devs[g];
             auto task = [&, g]() {
                 Dev& dd = *rt.devs[g];
@@ -868,6 +871,17 @@ void completer_main(Runtime* rtp) {
         rt.last_end_slot = slot;
         rt.last_end_dev = wv.first_dev;
         cudaEventElapsedTime(&ms_out, rt.ev_fwd_end[slot], rt.ev_wave[slot]);
+        float ms_fwd_max = 0, ms_gap_max = 0;  // over the participating replicas (each replica's events on its own device)
+        for (size_t g = 0; g < rt.devs.size(); ++g) {
+            if (!((wv.dev_mask >> g) & 1)) { rt.devs[g]->last_slot = -1; continue; }
+            Dev& dg = *rt.devs[g];
+            float f = 0, gp = 0;
+            if (cudaEventElapsedTime(&f, dg.ev_begin[slot], dg.ev_end[slot]) != cudaSuccess) { f = 0; cudaGetLastError(); }
+            if (dg.last_slot >= 0 && cudaEventElapsedTime(&gp, dg.ev_end[dg.last_slot], dg.ev_begin[slot]) != cudaSuccess) { gp = 0; cudaGetLastError(); }
+            dg.last_slot = slot;
+            ms_fwd_max = std::max(ms_fwd_max, f);
+            ms_gap_max = std::max(ms_gap_max, gp);
+        }
         {
             // rows of tickets that already failed or were shut down are not delivered: their owners may have freed `out`
             std::vector<const Segment*> live;
@@ -895,6 +909,8 @@ void completer_main(Runtime* rtp) {
             rt.stats.forward_us += ms_fwd * 1e3;
             rt.stats.gap_us += (ms_gap > 0 ? ms_gap : 0) * 1e3;
             rt.stats.d2h_us += ms_out * 1e3;
+            rt.stats.forward_max_us += ms_fwd_max * 1e3;
+            rt.stats.gap_max_us += ms_gap_max * 1e3;
         }
         {
             std::lock_guard<std::mutex> lk(rt.mu);
