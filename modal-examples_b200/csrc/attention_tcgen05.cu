@@ -159,6 +159,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
     g_attn_prog = smem_u32(prog);
 #endif
 
+    griddep_launch_dependents();
     const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
     const int lane = lane_id();
     const int nq_all = (S + QT - 1) / QT;
@@ -194,6 +195,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();  // the prologue above overlapped the previous kernel's tail; nothing it wrote (qkv, lens) has been read yet
 
     // (each role's code must be dominated by its own setmaxnreg for ptxas to allocate against the new budget)
     if (warp < 4) {
@@ -410,7 +412,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
         const uint32_t mr_base = smem_u32(smem + OFF_MR) + r * 4;
         const uint32_t mr_self = mr_base + w * QT * 4;
         const uint32_t ls_self = smem_u32(smem + OFF_LS) + (w * QT + r) * 8;
-        const uint32_t swz = static_cast<uint32_t>(r & 7);
         const bool obs = lane == 0 && ((warp & 3) == 0 || w == 0);
         const int ow = (warp & 3) == 0 ? w : 6 + (warp & 3);  // observer row: warp 0 of every warpgroup, all warps of warpgroup 0
         (void)obs; (void)ow;
@@ -648,8 +649,7 @@ cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tctx, con
     const int n_units = B * HEADS * (split ? nq : 1);
     int grid = n_units < sm_count ? n_units : sm_count;
     if (!pairs || grid < 2) {
-        attn::attention_kernel<<<grid, attn::NUM_THREADS, attn::SMEM_BYTES, stream>>>(tq, tctx, lens, S, split, n_units, dbg);
-        return cudaGetLastError();
+        return launch_pdl(attn::attention_kernel, dim3(grid), dim3(attn::NUM_THREADS), attn::SMEM_BYTES, stream, tq, tctx, lens, S, split, n_units, dbg);
     }
     grid &= ~1;
     cudaLaunchConfig_t cfg{};
@@ -657,13 +657,15 @@ cudaError_t launch_attention(const CUtensorMap& tq, const CUtensorMap& tctx, con
     cfg.blockDim = dim3(attn::NUM_THREADS);
     cfg.dynamicSmemBytes = attn::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, attn::attention_kernel, tq, tctx, lens, S, split, n_units, dbg);
 }
 

@@ -89,6 +89,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 12);
     float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS);
 
+    griddep_launch_dependents();
     const int warp = __shfl_sync(0xffffffff, threadIdx.x >> 5, 0);
     const int lane = lane_id();
     const uint32_t cta_rank = cluster_ctarank();
@@ -137,6 +138,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     cluster_sync_all();  // both CTAs' barriers are initialised before anyone signals across the pair
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    griddep_wait();  // everything above overlapped the previous kernel's tail; nothing it wrote has been read yet
 
     if (warp == 0) {
         if (elect_one()) {
@@ -446,8 +448,7 @@ static cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, con
     const int tiles = ((M + 2 * gemm::BM - 1) / (2 * gemm::BM)) * (N / gemm::BN);
     int pairs = sm_count / 2;
     if (tiles < pairs) pairs = tiles;
-    gemm::gemm_pair_kernel<EPI><<<2 * pairs, gemm::NUM_THREADS, gemm::SMEM_BYTES, stream>>>(ta, tb, tout, tlo, e, M, N, K, dbg_mode);
-    return cudaGetLastError();
+    return launch_pdl(gemm::gemm_pair_kernel<EPI>, dim3(2 * pairs), dim3(gemm::NUM_THREADS), gemm::SMEM_BYTES, stream, ta, tb, tout, tlo, e, M, N, K, dbg_mode);
 }
 
 cudaError_t gemm_init_device() {

@@ -103,3 +103,24 @@ cudaError_t launch_scatter(const int32_t* src_ids, const int32_t* src_lens, cons
                            cudaStream_t stream);
 
 }  // namespace b200
+
+#ifdef __CUDACC__
+#include <utility>
+// Launch with programmatic stream serialisation: the kernel's CTAs may be scheduled while the previous kernel of the
+// stream drains (see ptx.cuh: griddep_launch_dependents / griddep_wait); the kernel itself waits before it reads anything
+// the previous kernel wrote.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
+#endif

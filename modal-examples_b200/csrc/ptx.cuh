@@ -134,6 +134,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// ------------------------------------------------------------------------------------ programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (on SMs the previous kernel of the
+// stream has vacated) once every CTA of that kernel has executed launch_dependents or exited; griddep_wait() then blocks
+// until the previous grid has completed and its memory is visible.  Both are no-ops for a normally launched kernel.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------ TMA
 
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
