@@ -517,22 +517,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__
                 if (obs) ATT_STAMP(ow, g, 3);
                 float ls0 = 0.f, ls1 = 0.f;
                 uint32_t pk_prev[4];
+                // two scores per FFMA2 / FADD2 (same rounding, same summation order as the scalar loop: bit-identical)
+                const uint64_t k2 = pack_f32x2(kScaleLog2e, kScaleLog2e), nm2 = pack_f32x2(neg_ms, neg_ms);
+                uint64_t ls2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     uint32_t pk[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float x0 = fmaf(__uint_as_float(v[q * 8 + 2 * e]), kScaleLog2e, neg_ms);
-                        const float x1 = fmaf(__uint_as_float(v[q * 8 + 2 * e + 1]), kScaleLog2e, neg_ms);
+                        float x0, x1;
+                        unpack_f32x2(fma2_f32(pack_f32x2(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1])), k2, nm2), x0, x1);
                         const float p0 = ex2_approx(x0);
                         const float p1 = ex2_approx(x1);
-                        ls0 += p0;
-                        ls1 += p1;
+                        ls2 = add2_f32(ls2, pack_f32x2(p0, p1));
                         pk[e] = pack_half2(p0, p1);
                     }
                     if (q & 1) tmem_st_32x32b_x8(p_tm + (q >> 1) * 8, pk_prev[0], pk_prev[1], pk_prev[2], pk_prev[3], pk[0], pk[1], pk[2], pk[3]);
                     else { pk_prev[0] = pk[0]; pk_prev[1] = pk[1]; pk_prev[2] = pk[2]; pk_prev[3] = pk[3]; }
                 }
+                unpack_f32x2(ls2, ls0, ls1);
                 l_w += ls0 + ls1;
                 if (sb + NEXP >= U.nsb)  // this warpgroup's last sub-block of the tile
                     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(ls_self + (gtile % MAX_NQ) * (NEXP * QT * 8)), "f"(m_ref), "f"(l_w) : "memory");

@@ -64,6 +64,30 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return x * phi;
 }
 
+// the same erf-GELU on two values at a time: the FMA-pipe part as packed fp32 (FFMA2 / FMUL2 / FADD2: same rounding per element,
+// half the issue slots -- the GELU epilogue shares its SM sub-partitions with the TMA and MMA-issuing threads)
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+    const float a0 = fabsf(x0), a1 = fabsf(x1);
+    const uint64_t ax = pack_f32x2(a0, a1);
+    float u0, u1;
+    unpack_f32x2(fma2_f32(ax, pack_f32x2(0.3275911f * 0.70710678118654752f, 0.3275911f * 0.70710678118654752f), pack_f32x2(1.0f, 1.0f)), u0, u1);
+    float t0, t1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+    const uint64_t t = pack_f32x2(t0, t1);
+    uint64_t p = fma2_f32(pack_f32x2(0.5f * 1.061405429f, 0.5f * 1.061405429f), t, pack_f32x2(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+    p = fma2_f32(p, t, pack_f32x2(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+    p = fma2_f32(p, t, pack_f32x2(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+    p = fma2_f32(p, t, pack_f32x2(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+    float z0, z1;
+    unpack_f32x2(mul2_f32(mul2_f32(ax, pack_f32x2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f)), ax), z0, z1);
+    const uint64_t q2 = mul2_f32(mul2_f32(p, t), pack_f32x2(ex2_approx(z0), ex2_approx(z1)));
+    float q0, q1;
+    unpack_f32x2(q2, q0, q1);
+    const float phi0 = x0 >= 0.f ? 1.0f - q0 : q0, phi1 = x1 >= 0.f ? 1.0f - q1 : q1;
+    unpack_f32x2(mul2_f32(pack_f32x2(x0, x1), pack_f32x2(phi0, phi1)), x0, x1);
+}
+
 __device__ __forceinline__ float gelu_quick(float x) {
     // CLIP's quick_gelu: x * sigmoid(1.702 x) = x / (1 + 2^(-1.702 log2(e) x)): 2 MUFU + 3 FMA-pipe ops
     const float e = ex2_approx(x * (-1.702f * 1.4426950408889634f));
@@ -401,7 +425,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                     }
                     if constexpr (EPI == EPI_BIAS_GELU_F16) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+                        for (int j = 0; j < 32; j += 2) gelu_erf2(v[j], v[j + 1]);
                     }
                     if constexpr (EPI == EPI_BIAS_QGELU_F16) {
 #pragma unroll

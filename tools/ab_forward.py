@@ -17,7 +17,7 @@ e = model.embed(R.synth_ids(8, 512, 3))
 print(json.dumps(dict(prof=prof, total=sum(prof.values()), chk=float(np.abs(e).sum()))))
 '''
 for rep in range(2):
-    for key, lib in (("product", "libb200rt.so"), ("prev", "libb200rt_exp_prev.so")):
+    for key, lib in (("product", "libb200rt.so"), ("exp", "libb200rt_exp.so")):
         code = f"ROOT={ROOT!r}\nLIB={os.path.join(ROOT, 'modal-examples_b200', lib)!r}\n" + CHILD
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
         if r.returncode != 0:
