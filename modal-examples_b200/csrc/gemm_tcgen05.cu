@@ -49,23 +49,9 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 
-__device__ __forceinline__ float gelu_erf(float x) {
-    // x * Phi(x), erf by Abramowitz-Stegun 7.1.26 (abs err <= 1.5e-7): 2 MUFU + ~12 FMA-pipe ops
-    const float ax = fabsf(x);
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, ax, 1.0f)));
-    float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
-    p = fmaf(p, t, 0.5f * 1.421413741f);
-    p = fmaf(p, t, 0.5f * -0.284496736f);
-    p = fmaf(p, t, 0.5f * 0.254829592f);
-    const float e = ex2_approx((ax * (-0.5f * 1.4426950408889634f)) * ax);
-    const float q = (p * t) * e;
-    const float phi = x >= 0.f ? 1.0f - q : q;
-    return x * phi;
-}
-
-// the same erf-GELU on two values at a time: the FMA-pipe part as packed fp32 (FFMA2 / FMUL2 / FADD2: same rounding per element,
-// half the issue slots -- the GELU epilogue shares its SM sub-partitions with the TMA and MMA-issuing threads)
+// erf-GELU x * Phi(x) on two values at a time, erf by Abramowitz-Stegun 7.1.26 (abs err <= 1.5e-7): per value 2 MUFU (rcp, ex2)
+// + the FMA-pipe part as packed fp32 (FFMA2 / FMUL2: same rounding per element, half the issue slots -- the GELU epilogue shares
+// its SM sub-partitions with the TMA and MMA-issuing threads)
 __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
     const float a0 = fabsf(x0), a1 = fabsf(x1);
     const uint64_t ax = pack_f32x2(a0, a1);
