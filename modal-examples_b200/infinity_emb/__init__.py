@@ -127,14 +127,20 @@ class AsyncEmbeddingEngine:
                         n = max(1, torch.cuda.device_count())
                     b200rt.init(n)
             _runtime_refs += 1
-            e = _models.get(a.model_name_or_path)
-            if e is None:
-                geometry, blob, source = _load_clip(a)
-                if source is None:
-                    print(f"[infinity_emb/b200] no weights for {a.model_name_or_path!r} offline: seeded random init", file=sys.stderr)
-                else:
-                    print(f"[infinity_emb/b200] weights: {source}", file=sys.stderr)
-                e = _models[a.model_name_or_path] = {"model": b200rt.ImageEmbedModel(geometry, blob), "refs": 0, "image": geometry["image"]}
+            try:
+                e = _models.get(a.model_name_or_path)
+                if e is None:
+                    geometry, blob, source = _load_clip(a)
+                    if source is None:
+                        print(f"[infinity_emb/b200] no weights for {a.model_name_or_path!r} offline: seeded random init", file=sys.stderr)
+                    else:
+                        print(f"[infinity_emb/b200] weights: {source}", file=sys.stderr)
+                    e = _models[a.model_name_or_path] = {"model": b200rt.ImageEmbedModel(geometry, blob), "refs": 0, "image": geometry["image"]}
+            except BaseException:  # a failed load must not leave the runtime referenced by an engine that never ran
+                _runtime_refs -= 1
+                if _runtime_refs == 0 and _owns_runtime:
+                    b200rt.shutdown()
+                raise
             e["refs"] += 1
             self._entry = e
             self.running = True
